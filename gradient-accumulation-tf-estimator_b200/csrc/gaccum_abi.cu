@@ -1,0 +1,464 @@
+// gaccum_abi.cu -- host side of libgaccum.so: plan (slab layout + static tile table), the
+// scalar host logic of the reference graph, and the C ABI declared in include/gaccum.h.
+// No CPU compute path exists here on purpose: without a device every step call fails.
+#include <regex.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/gaccum.h"
+#include "gaccum_kernels.cuh"
+
+using namespace gaccum;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t e_ = (expr);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(GACCUM_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------
+constexpr int kCapSmall = 256;    // 4 KB pointer table   (MNIST, BERT-Small 73, BERT-Base 201)
+constexpr int kCapLarge = 1920;   // 30 KB pointer table  (BERT-Large 393, ...; CUDA >= 12.1 32 KB params)
+
+struct gaccum_plan {
+  int32_t T = 0;
+  int32_t device = -1;
+  gaccum_hparams hp{};
+  std::vector<int64_t> numel, offset;
+  std::vector<uint8_t> decay;
+  std::vector<TileDesc> tiles;
+  int64_t P = 0, padded = 0;
+  // device side
+  TileDesc* d_tiles = nullptr;
+  double* d_partials = nullptr;
+  float* d_stats = nullptr;
+  int num_sms = 0;
+  int max_grid = 0;
+  std::mutex mu;
+  std::map<const void*, int> grid_cache;   // kernel -> co-resident grid size
+};
+
+static int build_layout(gaccum_plan* pl) {
+  pl->offset.resize(pl->T);
+  int64_t off = 0, P = 0;
+  pl->tiles.clear();
+  for (int32_t t = 0; t < pl->T; ++t) {
+    const int64_t n = pl->numel[t];
+    if (n < 0) return fail(GACCUM_EINVAL, "numels[%d] = %lld is negative", t, (long long)n);
+    if (n >= (int64_t)1 << 32) return fail(GACCUM_EINVAL, "tensor %d has %lld elements; limit is 2^32-1", t, (long long)n);
+    pl->offset[t] = off;
+    for (int64_t to = 0; to < n; to += kTile) {
+      TileDesc d;
+      d.tensor_flags = (uint32_t)t | (pl->decay[t] ? 0x80000000u : 0u);
+      d.len = (uint32_t)std::min<int64_t>(kTile, n - to);
+      d.toff = (uint32_t)to;
+      const int64_t s32 = (off + to) / kSlabAlign;
+      if (s32 >= (int64_t)1 << 32) return fail(GACCUM_EINVAL, "slab too large (> 2^37 elements)");
+      d.soff32 = (uint32_t)s32;
+      pl->tiles.push_back(d);
+    }
+    P += n;
+    off += (n + kSlabAlign - 1) / kSlabAlign * kSlabAlign;
+  }
+  if (pl->tiles.size() >= (size_t)1 << 31) return fail(GACCUM_EINVAL, "too many tiles");
+  pl->P = P;
+  pl->padded = off;
+  return GACCUM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// scalars of one apply step
+// ------------------------------------------------------------------------------------------
+static Scalars make_scalars(const gaccum_hparams& hp, const gaccum_step_args* a) {
+  Scalars s{};
+  s.nf = a ? (float)a->accum_n : 1.0f;
+  s.lr = a ? a->lr : 0.0f;
+  s.b1 = (float)hp.beta1;
+  s.b2 = (float)hp.beta2;
+  s.eps = (float)hp.epsilon;
+  s.wd = (float)hp.weight_decay_rate;
+  s.clip = (float)hp.clip_norm;
+  if (hp.variant == GACCUM_ADAM_WEIGHT_DECAY) {
+    s.omb1 = (float)(1.0 - hp.beta1);   // optimization.py:152 -- Python double, then fp32
+    s.omb2 = (float)(1.0 - hp.beta2);   // optimization.py:154
+  } else {
+    volatile float o1 = 1.0f - s.b1, o2 = 1.0f - s.b2;   // ApplyAdam: T(1) - beta1()
+    s.omb1 = o1;
+    s.omb2 = o2;
+    if (a) {
+      volatile float t1 = 1.0f - a->beta2_power;
+      volatile float t2 = sqrtf(t1);
+      volatile float t3 = a->lr * t2;
+      volatile float t4 = 1.0f - a->beta1_power;
+      volatile float t5 = t3 / t4;
+      s.alpha = t5;
+    }
+  }
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------
+static int grid_for(gaccum_plan* pl, const void* fn, int* out) {
+  std::lock_guard<std::mutex> lk(pl->mu);
+  auto it = pl->grid_cache.find(fn);
+  if (it != pl->grid_cache.end()) { *out = it->second; return GACCUM_OK; }
+  int per_sm = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
+  if (per_sm < 1) return fail(GACCUM_ECUDA, "kernel does not fit on an SM");
+  int g = std::min(per_sm * pl->num_sms, pl->max_grid);
+  pl->grid_cache[fn] = g;
+  *out = g;
+  return GACCUM_OK;
+}
+
+template <int CAP>
+static int launch_accumulate(gaccum_plan* pl, KernelParams<CAP>& prm, cudaStream_t st) {
+  const void* fn = (const void*)&accumulate_kernel<CAP>;
+  int grid = 0;
+  if (int rc = grid_for(pl, fn, &grid)) return rc;
+  grid = std::max(1, std::min(grid, prm.num_tiles));
+  accumulate_kernel<CAP><<<grid, kThreads, 0, st>>>(prm);
+  CUDA_TRY(cudaGetLastError());
+  return GACCUM_OK;
+}
+
+template <int VARIANT, bool CLIP, bool HAS_G, int CAP>
+static int launch_apply_inst(gaccum_plan* pl, KernelParams<CAP>& prm, cudaStream_t st) {
+  const void* fn = (const void*)&apply_kernel<VARIANT, CLIP, HAS_G, CAP>;
+  int grid = 0;
+  if (int rc = grid_for(pl, fn, &grid)) return rc;
+  grid = std::max(1, std::min(grid, prm.num_tiles));
+  if (CLIP) {
+    void* args[] = {(void*)&prm};
+    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, 0, st));
+  } else {
+    apply_kernel<VARIANT, CLIP, HAS_G, CAP><<<grid, kThreads, 0, st>>>(prm);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return GACCUM_OK;
+}
+
+template <int CAP>
+static int launch_apply(gaccum_plan* pl, KernelParams<CAP>& prm, bool has_g, cudaStream_t st) {
+  const bool clip = pl->hp.clip_norm > 0.0;
+  const int key = (pl->hp.variant == GACCUM_ADAM ? 4 : 0) | (clip ? 2 : 0) | (has_g ? 1 : 0);
+  switch (key) {
+    case 0: return launch_apply_inst<0, false, false>(pl, prm, st);
+    case 1: return launch_apply_inst<0, false, true>(pl, prm, st);
+    case 2: return launch_apply_inst<0, true, false>(pl, prm, st);
+    case 3: return launch_apply_inst<0, true, true>(pl, prm, st);
+    case 4: return launch_apply_inst<1, false, false>(pl, prm, st);
+    case 5: return launch_apply_inst<1, false, true>(pl, prm, st);
+    case 6: return launch_apply_inst<1, true, false>(pl, prm, st);
+    default: return launch_apply_inst<1, true, true>(pl, prm, st);
+  }
+}
+
+static inline bool aligned16_host(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+
+static int check_compute(gaccum_plan* pl, const float* accum, const float* m, const float* v, bool need_mv) {
+  if (!pl) return fail(GACCUM_EINVAL, "plan is NULL");
+  if (pl->device < 0)
+    return fail(GACCUM_ENODEVICE, "layout-only plan (device=-1): libgaccum has no CPU fallback, a CUDA device is required");
+  if (!accum || !aligned16_host(accum)) return fail(GACCUM_EINVAL, "accum must be a 16-byte aligned device pointer");
+  if (need_mv && (!m || !v || !aligned16_host(m) || !aligned16_host(v)))
+    return fail(GACCUM_EINVAL, "m and v must be 16-byte aligned device pointers");
+  return GACCUM_OK;
+}
+
+template <int CAP>
+static void fill_common(gaccum_plan* pl, KernelParams<CAP>& prm, float* accum, float* m, float* v,
+                        const Scalars& sc) {
+  prm.tiles = pl->d_tiles;
+  prm.num_tiles = (int32_t)pl->tiles.size();
+  prm.accum = accum;
+  prm.m = m;
+  prm.v = v;
+  prm.partials = pl->d_partials;
+  prm.stats = pl->d_stats;
+  prm.sc = sc;
+}
+
+template <int CAP>
+static int fill_table(gaccum_plan* pl, PtrTable<CAP>& tab, const float* const* grads, float* const* params) {
+  for (int32_t t = 0; t < pl->T; ++t) {
+    tab.g[t] = grads ? grads[t] : nullptr;
+    if (params) {
+      if (!params[t] && pl->numel[t] > 0) return fail(GACCUM_EINVAL, "params[%d] is NULL", t);
+      tab.p[t] = params[t];
+    }
+  }
+  return GACCUM_OK;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0 && ok) cudaSetDevice(prev); }
+};
+
+template <int CAP>
+static int do_accumulate_tab(gaccum_plan* pl, const float* const* grads, float* accum, cudaStream_t st) {
+  KernelParams<CAP>* prm = new (std::nothrow) KernelParams<CAP>();
+  if (!prm) return fail(GACCUM_ENOMEM, "out of host memory");
+  fill_common(pl, *prm, accum, nullptr, nullptr, make_scalars(pl->hp, nullptr));
+  int rc = fill_table(pl, prm->tab, grads, nullptr);
+  if (rc == GACCUM_OK) rc = launch_accumulate(pl, *prm, st);
+  delete prm;
+  return rc;
+}
+
+template <int CAP>
+static int do_apply_tab(gaccum_plan* pl, const float* const* grads, float* const* params, float* accum,
+                        float* m, float* v, const gaccum_step_args* a, cudaStream_t st) {
+  KernelParams<CAP>* prm = new (std::nothrow) KernelParams<CAP>();
+  if (!prm) return fail(GACCUM_ENOMEM, "out of host memory");
+  fill_common(pl, *prm, accum, m, v, make_scalars(pl->hp, a));
+  int rc = fill_table(pl, prm->tab, grads, params);
+  if (rc == GACCUM_OK) rc = launch_apply(pl, *prm, grads != nullptr, st);
+  delete prm;
+  return rc;
+}
+
+static int check_args(const gaccum_step_args* a) {
+  if (!a) return fail(GACCUM_EINVAL, "args is NULL");
+  if (a->accum_n <= 0) return fail(GACCUM_EINVAL, "accum_n must be > 0 (got %d)", a->accum_n);
+  if (a->reserved != 0 || a->reserved2 != 0.0f) return fail(GACCUM_EINVAL, "reserved fields must be 0");
+  return GACCUM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int gaccum_version(void) { return GACCUM_VERSION; }
+const char* gaccum_last_error(void) { return g_err.c_str(); }
+
+int gaccum_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+// optimization.py:29-54, fp32 op order (volatile: one rounding per TF op, no double promotion)
+float gaccum_learning_rate(double init_lr, int64_t num_train_steps, int64_t num_warmup_steps,
+                           int64_t global_step) {
+  volatile float lr0 = (float)init_lr;
+  volatile float gs = (float)global_step;
+  volatile float ds = (float)num_train_steps;
+  if (gs > ds) gs = ds;
+  volatile float p = gs / ds;
+  volatile float omp = 1.0f - p;
+  volatile float lr = lr0 * omp;
+  if (num_warmup_steps) {
+    const int32_t gi = (int32_t)global_step, wi = (int32_t)num_warmup_steps;
+    volatile float pct = (float)gi / (float)wi;
+    volatile float wlr = (float)init_lr * pct;
+    volatile float isw = gi < wi ? 1.0f : 0.0f;
+    volatile float x = (1.0f - isw) * lr;
+    volatile float y = isw * wlr;
+    lr = x + y;
+  }
+  return lr;
+}
+
+int gaccum_is_apply_step(int64_t global_step, int32_t accum_n) {
+  if (accum_n <= 0) return 0;
+  return ((int32_t)global_step % accum_n) == 0;   // optimization.py:77,91
+}
+
+int gaccum_decay_mask(int32_t T, const char* const* names, double weight_decay_rate,
+                      const char* const* exclude, int32_t num_exclude, uint8_t* out) {
+  if (T < 0 || (T > 0 && (!names || !out))) return fail(GACCUM_EINVAL, "bad arguments to gaccum_decay_mask");
+  std::vector<regex_t> res((size_t)std::max(0, num_exclude));
+  int compiled = 0;
+  int rc = GACCUM_OK;
+  for (; compiled < num_exclude; ++compiled) {
+    if (!exclude || !exclude[compiled] || regcomp(&res[compiled], exclude[compiled], REG_EXTENDED | REG_NOSUB) != 0) {
+      rc = fail(GACCUM_EINVAL, "exclude[%d] is not a valid regular expression", compiled);
+      break;
+    }
+  }
+  if (rc == GACCUM_OK) {
+    for (int32_t t = 0; t < T; ++t) {
+      std::string nm = names[t] ? names[t] : "";
+      // optimization.py:189-194 -- strip ":<digits>"
+      size_t c = nm.rfind(':');
+      if (c != std::string::npos && c + 1 < nm.size() &&
+          std::all_of(nm.begin() + c + 1, nm.end(), [](char ch) { return ch >= '0' && ch <= '9'; }))
+        nm.resize(c);
+      uint8_t use = weight_decay_rate != 0.0;      // optimization.py:181 `if not self.weight_decay_rate`
+      for (int i = 0; use && i < num_exclude; ++i)
+        if (regexec(&res[i], nm.c_str(), 0, nullptr, 0) == 0) use = 0;   // :183-186 re.search
+      out[t] = use;
+    }
+  }
+  for (int i = 0; i < compiled; ++i) regfree(&res[i]);
+  return rc;
+}
+
+int gaccum_plan_create(gaccum_plan** out, int32_t T, const int64_t* numels, const uint8_t* decay,
+                       const gaccum_hparams* hp, int32_t device) {
+  if (!out) return fail(GACCUM_EINVAL, "out is NULL");
+  *out = nullptr;
+  if (T < 0 || (T > 0 && !numels)) return fail(GACCUM_EINVAL, "bad tensor list");
+  if (!hp) return fail(GACCUM_EINVAL, "hp is NULL");
+  if (hp->variant != GACCUM_ADAM_WEIGHT_DECAY && hp->variant != GACCUM_ADAM)
+    return fail(GACCUM_EINVAL, "unknown optimizer variant %d", hp->variant);
+  if (hp->reserved != 0) return fail(GACCUM_EINVAL, "reserved fields must be 0");
+  if (T > kCapLarge)
+    return fail(GACCUM_EINVAL, "%d tensors exceed the %d-entry pointer table; use the packed entry point with one slab", T, kCapLarge);
+  gaccum_plan* pl = new (std::nothrow) gaccum_plan();
+  if (!pl) return fail(GACCUM_ENOMEM, "out of host memory");
+  pl->T = T;
+  pl->hp = *hp;
+  pl->numel.assign(numels, numels + T);
+  pl->decay.assign((size_t)T, 0);
+  if (hp->variant == GACCUM_ADAM_WEIGHT_DECAY && decay) pl->decay.assign(decay, decay + T);
+  if (int rc = build_layout(pl)) { delete pl; return rc; }
+  pl->device = -1;
+  if (device >= 0) {
+    int n = gaccum_device_count();
+    if (device >= n) { delete pl; return fail(GACCUM_ENODEVICE, "CUDA device %d requested but %d device(s) visible; libgaccum has no CPU fallback", device, n); }
+    DeviceGuard guard(device);
+    cudaDeviceProp prop{};
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e == cudaSuccess && !prop.cooperativeLaunch) e = cudaErrorNotSupported;
+    const size_t tb = std::max<size_t>(1, pl->tiles.size()) * sizeof(TileDesc);
+    pl->num_sms = prop.multiProcessorCount;
+    pl->max_grid = pl->num_sms * 16;
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_tiles, tb);
+    if (e == cudaSuccess && !pl->tiles.empty())
+      e = cudaMemcpy(pl->d_tiles, pl->tiles.data(), pl->tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_partials, sizeof(double) * (size_t)pl->max_grid);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_stats, sizeof(gaccum_stats));
+    if (e == cudaSuccess) e = cudaMemset(pl->d_stats, 0, sizeof(gaccum_stats));
+    if (e != cudaSuccess) {
+      cudaFree(pl->d_tiles); cudaFree(pl->d_partials); cudaFree(pl->d_stats);
+      delete pl;
+      return fail(GACCUM_ECUDA, "plan device setup failed: %s", cudaGetErrorString(e));
+    }
+    pl->device = device;
+  }
+  *out = pl;
+  return GACCUM_OK;
+}
+
+int gaccum_plan_destroy(gaccum_plan* pl) {
+  if (!pl) return GACCUM_OK;
+  if (pl->device >= 0) {
+    DeviceGuard guard(pl->device);
+    cudaFree(pl->d_tiles); cudaFree(pl->d_partials); cudaFree(pl->d_stats);
+  }
+  delete pl;
+  return GACCUM_OK;
+}
+
+int64_t gaccum_padded_size(const gaccum_plan* pl) { return pl ? pl->padded : fail(GACCUM_EINVAL, "plan is NULL"); }
+int32_t gaccum_num_tensors(const gaccum_plan* pl) { return pl ? pl->T : fail(GACCUM_EINVAL, "plan is NULL"); }
+int64_t gaccum_num_elements(const gaccum_plan* pl) { return pl ? pl->P : fail(GACCUM_EINVAL, "plan is NULL"); }
+int32_t gaccum_num_tiles(const gaccum_plan* pl) { return pl ? (int32_t)pl->tiles.size() : fail(GACCUM_EINVAL, "plan is NULL"); }
+
+int gaccum_offsets(const gaccum_plan* pl, int64_t* out) {
+  if (!pl || (!out && pl->T > 0)) return fail(GACCUM_EINVAL, "bad arguments to gaccum_offsets");
+  std::copy(pl->offset.begin(), pl->offset.end(), out);
+  return GACCUM_OK;
+}
+
+int64_t gaccum_algorithmic_bytes(const gaccum_plan* pl, int32_t is_apply) {
+  if (!pl) return fail(GACCUM_EINVAL, "plan is NULL");
+  // accumulate: read G, read a, write a.  apply: read G,a,p,m,v + write p,m,v,a  
+  return pl->P * (is_apply ? 36 : 12);
+}
+
+int gaccum_accumulate(gaccum_plan* pl, const float* const* grads, float* accum, gaccum_stream_t stream) {
+  if (int rc = check_compute(pl, accum, nullptr, nullptr, false)) return rc;
+  if (!grads) return fail(GACCUM_EINVAL, "grads is NULL");
+  DeviceGuard guard(pl->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  return pl->T <= kCapSmall ? do_accumulate_tab<kCapSmall>(pl, grads, accum, st)
+                            : do_accumulate_tab<kCapLarge>(pl, grads, accum, st);
+}
+
+int gaccum_apply(gaccum_plan* pl, const float* const* grads, float* const* params, float* accum,
+                 float* m, float* v, const gaccum_step_args* a, gaccum_stream_t stream) {
+  if (int rc = check_compute(pl, accum, m, v, true)) return rc;
+  if (int rc = check_args(a)) return rc;
+  if (!params) return fail(GACCUM_EINVAL, "params is NULL");
+  DeviceGuard guard(pl->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  return pl->T <= kCapSmall ? do_apply_tab<kCapSmall>(pl, grads, params, accum, m, v, a, st)
+                            : do_apply_tab<kCapLarge>(pl, grads, params, accum, m, v, a, st);
+}
+
+int gaccum_step(gaccum_plan* pl, const float* const* grads, float* const* params, float* accum,
+                float* m, float* v, const gaccum_step_args* a, gaccum_stream_t stream) {
+  if (int rc = check_args(a)) return rc;
+  if (!grads) return fail(GACCUM_EINVAL, "grads is NULL");
+  if (gaccum_is_apply_step(a->global_step, a->accum_n)) return gaccum_apply(pl, grads, params, accum, m, v, a, stream);
+  return gaccum_accumulate(pl, grads, accum, stream);
+}
+
+int gaccum_step_packed(gaccum_plan* pl, const float* grad_slab, float* param_slab, float* accum,
+                       float* m, float* v, const gaccum_step_args* a, int32_t force_branch,
+                       gaccum_stream_t stream) {
+  if (int rc = check_args(a)) return rc;
+  const bool apply = force_branch < 0 ? gaccum_is_apply_step(a->global_step, a->accum_n) != 0 : force_branch != 0;
+  if (int rc = check_compute(pl, accum, m, v, apply)) return rc;
+  if (grad_slab && !aligned16_host(grad_slab)) return fail(GACCUM_EINVAL, "grad_slab must be 16-byte aligned");
+  DeviceGuard guard(pl->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  KernelParams<0> prm{};
+  fill_common(pl, prm, accum, m, v, make_scalars(pl->hp, a));
+  prm.tab.g = grad_slab;
+  prm.tab.p = param_slab;
+  if (!apply) {
+    if (!grad_slab) return fail(GACCUM_EINVAL, "grad_slab is NULL on an accumulate step");
+    return launch_accumulate(pl, prm, st);
+  }
+  if (!param_slab || !aligned16_host(param_slab)) return fail(GACCUM_EINVAL, "param_slab must be a 16-byte aligned device pointer");
+  return launch_apply(pl, prm, grad_slab != nullptr, st);
+}
+
+int gaccum_read_stats(gaccum_plan* pl, gaccum_stats* host_out, gaccum_stream_t stream) {
+  if (!pl || !host_out) return fail(GACCUM_EINVAL, "bad arguments to gaccum_read_stats");
+  if (pl->device < 0) return fail(GACCUM_ENODEVICE, "layout-only plan has no stats");
+  DeviceGuard guard(pl->device);
+  CUDA_TRY(cudaMemcpyAsync(host_out, pl->d_stats, sizeof(gaccum_stats), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return GACCUM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,422 @@
+// gaccum_kernels.cuh -- sm_100a kernels of the gradient-accumulation train_op.
+//
+// Two kernels, both persistent (grid = SMs x resident CTAs) and grid-striding over a static
+// tile table, so the work split -- and therefore every reduction -- is deterministic:
+//
+//   accumulate_kernel   a += G                                   optimization.py:81,93   (12 B/elem)
+//   apply_kernel        a' = a + G; n = a'/N; [gn = ||n||; s = clip scale; c = n*s];
+//                       AdamWeightDecay | Adam update of p, m, v; a = 0
+//                                                 optimization.py:80-88, 128-177        (36 B/elem)
+//
+// The apply kernel needs the global norm of ALL tensors before it can update ANY element, so
+// with clipping on it is a cooperative launch with two passes separated by one grid barrier:
+//   pass 1 streams G and a, writes a' back in place and reduces sum(n^2)
+//          (thread fp32 -> warp shuffle -> shared memory -> one fp64 partial per CTA);
+//   barrier; every CTA sums the per-CTA partials in the same fixed order (bit-identical s);
+//   pass 2 walks the CTA's tiles in REVERSE order, so the a' lines written last in pass 1 are
+//          read first and are served from the 126 MB L2 instead of HBM.
+// Arithmetic uses round-to-nearest intrinsics (__fmul_rn, __fadd_rn, __fdiv_rn, __fsqrt_rn)
+// so nvcc cannot contract mul+add into FMA: the reference graph is un-fused, one rounding per
+// TF op, and we reproduce it bit for bit (the kernel is HBM-bound, the extra flops are free).
+#pragma once
+
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gaccum {
+namespace cg = cooperative_groups;
+
+constexpr int kThreads = 256;                    // 8 warps per CTA
+constexpr int kUnroll = 2;                       // 128-bit vectors per thread per stream per tile
+constexpr int kTile = kThreads * 4 * kUnroll;    // 2048 elements = 8 KB per stream
+constexpr int kSlabAlign = 32;                   // tensors start at multiples of 32 elements (128 B)
+
+// One unit of work: <= kTile consecutive elements of ONE tensor (so pointers and the decay flag
+// are tile-uniform).  16 bytes, read with a single LDG.128.
+struct __align__(16) TileDesc {
+  uint32_t tensor_flags;   // bits 0..30 tensor index, bit 31 = apply weight decay (optimization.py:166)
+  uint32_t len;            // elements in this tile (1..kTile)
+  uint32_t toff;           // element offset inside the tensor (multiple of kTile)
+  uint32_t soff32;         // element offset inside the slabs, in units of 32 elements
+};
+
+// Scattered inputs arrive as a pointer table that lives in the kernel-parameter (constant)
+// space: no device-side table to keep in sync, launches stay re-entrant and graph-capturable.
+// CAP = 0 is the packed layout (grads/params are slabs with the same offsets as accum).
+template <int CAP>
+struct PtrTable {
+  const float* g[CAP];
+  float* p[CAP];
+};
+template <>
+struct PtrTable<0> {
+  const float* g;
+  float* p;
+};
+
+struct Scalars {
+  float nf;      // fp32(N)                                   optimization.py:83
+  float lr;      // learning rate of this micro-step          optimization.py:29-54
+  float b1, b2;  // fp32(beta)                                optimization.py:151,153
+  float omb1;    // A: fp32(1.0 - beta1) from double (:152);  B: 1.0f - fp32(beta1)
+  float omb2;
+  float eps;     //                                           optimization.py:157
+  float wd;      //                                           optimization.py:167
+  float clip;    //                                           optimization.py:84
+  float alpha;   // B only: lr*sqrt(1-b2^t)/(1-b1^t)          TF1 ApplyAdam
+};
+
+template <int CAP>
+struct KernelParams {
+  const TileDesc* tiles;
+  int32_t num_tiles;
+  float* accum;
+  float* m;
+  float* v;
+  double* partials;   // one per CTA (apply with clip)
+  float* stats;       // gaccum_stats
+  Scalars sc;
+  PtrTable<CAP> tab;
+};
+
+// ---------------------------------------------------------------------------------------------
+// memory helpers: G is read exactly once -> streaming (evict-first) loads; zeroing the
+// accumulator is a streaming store; state uses the default policy.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+
+template <int CAP>
+__device__ __forceinline__ const float* grad_ptr(const PtrTable<CAP>& tab, const TileDesc& d) {
+  if constexpr (CAP == 0) {
+    return tab.g ? tab.g + (size_t)d.soff32 * kSlabAlign : nullptr;
+  } else {
+    const float* b = tab.g[d.tensor_flags & 0x7fffffffu];
+    return b ? b + d.toff : nullptr;
+  }
+}
+template <int CAP>
+__device__ __forceinline__ float* param_ptr(const PtrTable<CAP>& tab, const TileDesc& d) {
+  if constexpr (CAP == 0) {
+    return tab.p + (size_t)d.soff32 * kSlabAlign;
+  } else {
+    return tab.p[d.tensor_flags & 0x7fffffffu] + d.toff;
+  }
+}
+__device__ __forceinline__ bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+
+// ---------------------------------------------------------------------------------------------
+// per-element math, one rounding per reference op
+// ---------------------------------------------------------------------------------------------
+// optimization.py:83  (1.0*a)/N  -- the multiply by 1.0 is exact
+__device__ __forceinline__ float normalize(float a, float nf) { return __fdiv_rn(a, nf); }
+
+template <int VARIANT>
+__device__ __forceinline__ void adam_elem(float c, float& p, float& m, float& v, bool decay,
+                                          const Scalars& sc) {
+  if constexpr (VARIANT == 0) {
+    // optimization.py:151-171
+    const float m2 = __fadd_rn(__fmul_rn(sc.b1, m), __fmul_rn(sc.omb1, c));
+    const float v2 = __fadd_rn(__fmul_rn(sc.b2, v), __fmul_rn(sc.omb2, __fmul_rn(c, c)));
+    float u = __fdiv_rn(m2, __fadd_rn(__fsqrt_rn(v2), sc.eps));
+    if (decay) u = __fadd_rn(u, __fmul_rn(sc.wd, p));
+    p = __fsub_rn(p, __fmul_rn(sc.lr, u));
+    m = m2;
+    v = v2;
+  } else {
+    // TF1 ApplyAdam: m += (g-m)(1-b1); v += (g*g-v)(1-b2); var -= (m*alpha)/(sqrt(v)+eps)
+    const float m2 = __fadd_rn(m, __fmul_rn(__fsub_rn(c, m), sc.omb1));
+    const float v2 = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(c, c), v), sc.omb2));
+    p = __fsub_rn(p, __fdiv_rn(__fmul_rn(m2, sc.alpha), __fadd_rn(__fsqrt_rn(v2), sc.eps)));
+    m = m2;
+    v = v2;
+  }
+}
+
+// tf.clip_by_global_norm (TF 1.15): scale = clip * min(1/gn, 1/clip) + (gn - gn)
+__device__ __forceinline__ float clip_scale(float gn, float clip) {
+  const float inv = __fdiv_rn(1.0f, gn);
+  const float invc = __fdiv_rn(1.0f, clip);
+  float mn = inv < invc ? inv : invc;
+  if (inv != inv) mn = inv;
+  return __fadd_rn(__fmul_rn(clip, mn), __fsub_rn(gn, gn));
+}
+
+// ---------------------------------------------------------------------------------------------
+// accumulate: a += G                                                   optimization.py:81,93
+// ---------------------------------------------------------------------------------------------
+template <int CAP>
+__device__ __forceinline__ void accumulate_tile(const TileDesc d, const KernelParams<CAP>& prm) {
+  const float* __restrict__ g = grad_ptr(prm.tab, d);
+  if (g == nullptr) return;   // optimization.py:132 -- tensors without a gradient are skipped
+  float* __restrict__ a = prm.accum + (size_t)d.soff32 * kSlabAlign;
+  const uint32_t len = d.len, tid = threadIdx.x;
+  if (aligned16(g)) {
+    const uint32_t nvec = len >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4* a4 = reinterpret_cast<float4*>(a);
+    float4 vg[kUnroll], va[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint32_t i = u * kThreads + tid;
+      if (i < nvec) { vg[u] = ld_stream(g4 + i); va[u] = a4[i]; }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint32_t i = u * kThreads + tid;
+      if (i < nvec) {
+        va[u].x = __fadd_rn(va[u].x, vg[u].x); va[u].y = __fadd_rn(va[u].y, vg[u].y);
+        va[u].z = __fadd_rn(va[u].z, vg[u].z); va[u].w = __fadd_rn(va[u].w, vg[u].w);
+        a4[i] = va[u];
+      }
+    }
+    const uint32_t i = (nvec << 2) + tid;      // < 4 trailing elements
+    if (i < len) a[i] = __fadd_rn(a[i], ld_stream(g + i));
+  } else {
+    for (uint32_t i = tid; i < len; i += kThreads) a[i] = __fadd_rn(a[i], ld_stream(g + i));
+  }
+}
+
+template <int CAP>
+__global__ void __launch_bounds__(kThreads)
+accumulate_kernel(const __grid_constant__ KernelParams<CAP> prm) {
+  int t = blockIdx.x;
+  if (t >= prm.num_tiles) return;
+  TileDesc d = prm.tiles[t];
+  while (true) {
+    const int tn = t + gridDim.x;
+    TileDesc dn;
+    if (tn < prm.num_tiles) dn = prm.tiles[tn];   // prefetch the next descriptor
+    accumulate_tile(d, prm);
+    if (tn >= prm.num_tiles) break;
+    t = tn; d = dn;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    prm.stats[0] = 0.f; prm.stats[1] = prm.sc.lr; prm.stats[2] = 0.f; prm.stats[3] = 1.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// apply, pass 1 (clip only): a' = a + G written back, returns acc + sum((a'/N)^2) over the tile
+// ---------------------------------------------------------------------------------------------
+template <bool HAS_G, int CAP>
+__device__ __forceinline__ float norm_tile(const TileDesc d, const KernelParams<CAP>& prm, float acc) {
+  const float* __restrict__ g = nullptr;
+  if constexpr (HAS_G) g = grad_ptr(prm.tab, d);
+  float* __restrict__ a = prm.accum + (size_t)d.soff32 * kSlabAlign;
+  const uint32_t len = d.len, tid = threadIdx.x;
+  const float nf = prm.sc.nf;
+  if (g == nullptr || aligned16(g)) {
+    const uint32_t nvec = len >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4* a4 = reinterpret_cast<float4*>(a);
+    float4 vg[kUnroll], va[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint32_t i = u * kThreads + tid;
+      if (i < nvec) { va[u] = a4[i]; if (g) vg[u] = ld_stream(g4 + i); }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint32_t i = u * kThreads + tid;
+      if (i < nvec) {
+        if (g) {
+          va[u].x = __fadd_rn(va[u].x, vg[u].x); va[u].y = __fadd_rn(va[u].y, vg[u].y);
+          va[u].z = __fadd_rn(va[u].z, vg[u].z); va[u].w = __fadd_rn(va[u].w, vg[u].w);
+          a4[i] = va[u];
+        }
+        const float nx = normalize(va[u].x, nf), ny = normalize(va[u].y, nf),
+                    nz = normalize(va[u].z, nf), nw = normalize(va[u].w, nf);
+        acc = fmaf(nx, nx, acc); acc = fmaf(ny, ny, acc); acc = fmaf(nz, nz, acc); acc = fmaf(nw, nw, acc);
+      }
+    }
+    const uint32_t i = (nvec << 2) + tid;
+    if (i < len) {
+      float x = a[i];
+      if (g) { x = __fadd_rn(x, ld_stream(g + i)); a[i] = x; }
+      const float n = normalize(x, nf);
+      acc = fmaf(n, n, acc);
+    }
+  } else {
+    for (uint32_t i = tid; i < len; i += kThreads) {
+      const float x = __fadd_rn(a[i], ld_stream(g + i));
+      a[i] = x;
+      const float n = normalize(x, nf);
+      acc = fmaf(n, n, acc);
+    }
+  }
+  return acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// apply, update pass.  LOAD_G: single-pass mode (no clip) adds G here; after pass 1 it is false.
+// ---------------------------------------------------------------------------------------------
+template <int VARIANT, bool CLIP, bool LOAD_G, int CAP>
+__device__ __forceinline__ void update_tile(const TileDesc d, const KernelParams<CAP>& prm, const float s) {
+  const float* __restrict__ g = nullptr;
+  if constexpr (LOAD_G) g = grad_ptr(prm.tab, d);
+  const size_t soff = (size_t)d.soff32 * kSlabAlign;
+  float* __restrict__ a = prm.accum + soff;
+  float* __restrict__ m = prm.m + soff;
+  float* __restrict__ v = prm.v + soff;
+  float* __restrict__ p = param_ptr(prm.tab, d);
+  const bool decay = (d.tensor_flags >> 31) != 0;
+  const uint32_t len = d.len, tid = threadIdx.x;
+  const Scalars& sc = prm.sc;
+
+  auto elem = [&](float ax, float gx, float& px, float& mx, float& vx) {
+    if (LOAD_G) ax = __fadd_rn(ax, gx);               // optimization.py:81 (gx = 0 never used: see callers)
+    float c = normalize(ax, sc.nf);                    // :83
+    if (CLIP) c = __fmul_rn(c, s);                     // :84
+    adam_elem<VARIANT>(c, px, mx, vx, decay, sc);      // :85
+  };
+
+  if (aligned16(p) && (g == nullptr || aligned16(g))) {
+    const uint32_t nvec = len >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4* a4 = reinterpret_cast<float4*>(a);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    float4* p4 = reinterpret_cast<float4*>(p);
+    float4 va[kUnroll], vg[kUnroll], vp[kUnroll], vm[kUnroll], vv[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint32_t i = u * kThreads + tid;
+      if (i < nvec) {
+        va[u] = a4[i]; vp[u] = p4[i]; vm[u] = m4[i]; vv[u] = v4[i];
+        if (LOAD_G && g) vg[u] = ld_stream(g4 + i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint32_t i = u * kThreads + tid;
+      if (i < nvec) {
+        if (LOAD_G && g) {
+          elem(va[u].x, vg[u].x, vp[u].x, vm[u].x, vv[u].x); elem(va[u].y, vg[u].y, vp[u].y, vm[u].y, vv[u].y);
+          elem(va[u].z, vg[u].z, vp[u].z, vm[u].z, vv[u].z); elem(va[u].w, vg[u].w, vp[u].w, vm[u].w, vv[u].w);
+        } else {
+          // no gradient for this tile: a + 0 would turn -0 into +0 only; skip the add entirely
+          auto e0 = [&](float ax, float& px, float& mx, float& vx) {
+            float c = normalize(ax, sc.nf);
+            if (CLIP) c = __fmul_rn(c, s);
+            adam_elem<VARIANT>(c, px, mx, vx, decay, sc);
+          };
+          e0(va[u].x, vp[u].x, vm[u].x, vv[u].x); e0(va[u].y, vp[u].y, vm[u].y, vv[u].y);
+          e0(va[u].z, vp[u].z, vm[u].z, vv[u].z); e0(va[u].w, vp[u].w, vm[u].w, vv[u].w);
+        }
+        p4[i] = vp[u]; m4[i] = vm[u]; v4[i] = vv[u];
+        __stcs(a4 + i, make_float4(0.f, 0.f, 0.f, 0.f));   // optimization.py:86-87
+      }
+    }
+    const uint32_t i = (nvec << 2) + tid;
+    if (i < len) {
+      float ax = a[i], px = p[i], mx = m[i], vx = v[i];
+      if (LOAD_G && g) ax = __fadd_rn(ax, ld_stream(g + i));
+      float c = normalize(ax, sc.nf);
+      if (CLIP) c = __fmul_rn(c, s);
+      adam_elem<VARIANT>(c, px, mx, vx, decay, sc);
+      p[i] = px; m[i] = mx; v[i] = vx; a[i] = 0.f;
+    }
+  } else {
+    for (uint32_t i = tid; i < len; i += kThreads) {
+      float ax = a[i], px = p[i], mx = m[i], vx = v[i];
+      if (LOAD_G && g) ax = __fadd_rn(ax, ld_stream(g + i));
+      float c = normalize(ax, sc.nf);
+      if (CLIP) c = __fmul_rn(c, s);
+      adam_elem<VARIANT>(c, px, mx, vx, decay, sc);
+      p[i] = px; m[i] = mx; v[i] = vx; a[i] = 0.f;
+    }
+  }
+}
+
+// Deterministic CTA reduction of one float per thread -> double in thread 0.
+__device__ __forceinline__ double block_reduce_to_double(float x, float* smem /* kThreads/32 */) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x = __fadd_rn(x, __shfl_xor_sync(0xffffffffu, x, o));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) smem[warp] = x;
+  __syncthreads();
+  double tot = 0.0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) tot += (double)smem[w];
+  }
+  return tot;
+}
+
+template <int VARIANT, bool CLIP, bool HAS_G, int CAP>
+__global__ void __launch_bounds__(kThreads)
+apply_kernel(const __grid_constant__ KernelParams<CAP> prm) {
+  __shared__ float red[kThreads / 32];
+  __shared__ float s_bcast[2];
+  const int nt = prm.num_tiles;
+  float s = 1.0f, gn = 0.0f;
+
+  if constexpr (CLIP) {
+    // ---- pass 1: a' = a + G (written back), sum of squares of a'/N -----------------------
+    float acc = 0.f;
+    int t = blockIdx.x;
+    if (t < nt) {
+      TileDesc d = prm.tiles[t];
+      while (true) {
+        const int tn = t + gridDim.x;
+        TileDesc dn;
+        if (tn < nt) dn = prm.tiles[tn];
+        acc = norm_tile<HAS_G>(d, prm, acc);
+        if (tn >= nt) break;
+        t = tn; d = dn;
+      }
+    }
+    const double part = block_reduce_to_double(acc, red);
+    if (threadIdx.x == 0) prm.partials[blockIdx.x] = part;
+    cg::this_grid().sync();
+    // ---- every CTA combines the per-CTA partials in the same fixed order -----------------
+    if (threadIdx.x < 32) {
+      double tot = 0.0;
+      for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) tot += __ldcg(prm.partials + i);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+      if (threadIdx.x == 0) {
+        // tf.linalg.global_norm: sqrt(2 * sum_i l2_loss(n_i)) == sqrt(sum n^2), fp32
+        const float g_norm = __fsqrt_rn((float)tot);
+        s_bcast[0] = clip_scale(g_norm, prm.sc.clip);
+        s_bcast[1] = g_norm;
+      }
+    }
+    __syncthreads();
+    s = s_bcast[0]; gn = s_bcast[1];
+    // ---- pass 2, reverse order: most recently written a' lines first (L2 hits) ----------
+    if (blockIdx.x < nt) {
+      int t2 = blockIdx.x + ((nt - 1 - blockIdx.x) / gridDim.x) * gridDim.x;   // my last tile
+      TileDesc d = prm.tiles[t2];
+      while (true) {
+        const int tn = t2 - (int)gridDim.x;
+        TileDesc dn;
+        if (tn >= 0) dn = prm.tiles[tn];
+        update_tile<VARIANT, true, false>(d, prm, s);
+        if (tn < 0) break;
+        t2 = tn; d = dn;
+      }
+    }
+  } else {
+    // ---- no clipping: one pass, 36 B/elem ------------------------------------------------
+    int t = blockIdx.x;
+    if (t < nt) {
+      TileDesc d = prm.tiles[t];
+      while (true) {
+        const int tn = t + gridDim.x;
+        TileDesc dn;
+        if (tn < nt) dn = prm.tiles[tn];
+        update_tile<VARIANT, false, HAS_G>(d, prm, 1.0f);
+        if (tn >= nt) break;
+        t = tn; d = dn;
+      }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    prm.stats[0] = 1.f; prm.stats[1] = prm.sc.lr; prm.stats[2] = gn; prm.stats[3] = s;
+  }
+}
+
+}  // namespace gaccum

@@ -1,0 +1,131 @@
+"""CUDA path (through the C ABI) vs the CPU oracle on identical seeded inputs."""
+import numpy as np
+import pytest
+
+import oracle_np as onp
+from common import make_grads, make_params, oracle_for, rel_err
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+BERT_SCHED = dict(init_lr=2e-5, num_train_steps=207900, num_warmup_steps=20790)
+
+TOY = [("bert/embeddings/word_embeddings", (1000, 33)), ("bert/embeddings/LayerNorm/beta", (33,)),
+       ("bert/embeddings/LayerNorm/gamma", (33,)), ("l0/attention/self/query/kernel", (64, 64)),
+       ("l0/attention/self/query/bias", (64,)), ("big/kernel", (3, 4099)), ("output_bias", (2,)),
+       ("one", (1,)), ("l1/dense/kernel", (2048,)), ("l1/dense/bias", (2049,))]
+
+
+def _gpu_op(manifest, params, hp_kind, N, sched):
+    import gaccum_b200 as g
+    from gaccum_b200.train_op import GaccumTrainOp
+    dev = torch.device("cuda:0")
+    tp = [torch.from_numpy(p.copy()).to(dev) for p in params]
+    if hp_kind == "bert":
+        hp = g.HParams.bert()
+    elif hp_kind == "bert_noclip":
+        hp = g.HParams.bert(); hp.clip_norm = 0.0
+    else:
+        hp = g.HParams.tf_adam()
+    if "constant_lr" in sched:
+        lr_fn = lambda s: sched["constant_lr"]
+    else:
+        lr_fn = lambda s: g.learning_rate(sched["init_lr"], sched["num_train_steps"], sched["num_warmup_steps"], s)
+    return GaccumTrainOp(tp, [n for n, _ in manifest], hp, N, lr_fn), tp
+
+
+def _oracle_hp(kind):
+    if kind == "bert":
+        return onp.HParams.bert()
+    if kind == "bert_noclip":
+        hp = onp.HParams.bert(); hp.clip_norm = 0.0; return hp
+    return onp.HParams.tf_adam()
+
+
+def _compare(op, tp, ref, bitexact, tol=1e-5):
+    worst = 0.0
+    for i in range(len(tp)):
+        for name, got, exp in (("p", tp[i].cpu().numpy(), ref.params[i]),
+                               ("m", op.m_view(i).cpu().numpy(), ref.m[i]),
+                               ("v", op.v_view(i).cpu().numpy(), ref.v[i]),
+                               ("a", op.accum_view(i).cpu().numpy(), ref.accum[i])):
+            if bitexact:
+                assert np.array_equal(got, exp, equal_nan=True), f"tensor {i} {name} not bit-identical"
+            else:
+                e = rel_err(got, exp)
+                worst = max(worst, e)
+                assert e <= tol, f"tensor {i} {name}: rel err {e}"
+                assert np.allclose(got, exp, rtol=tol, atol=1e-8, equal_nan=True)
+    return worst
+
+
+@pytest.mark.parametrize("hp_kind,sigma,sched", [
+    ("bert", 1e-4, BERT_SCHED),                      # unclipped: scale == 1.0 -> bit-exact
+    ("bert", 1.0, BERT_SCHED),                       # clipped
+    ("bert", 1e-2, dict(BERT_SCHED, num_warmup_steps=0)),
+    ("bert_noclip", 1e-2, dict(BERT_SCHED, num_warmup_steps=0)),
+    ("adam", 1e-2, dict(constant_lr=1e-4)),          # distributedExample/02 optimizer
+])
+@pytest.mark.parametrize("N", [1, 3, 4])
+def test_trajectory_matches_oracle(hp_kind, sigma, sched, N):
+    rng = np.random.default_rng(7)
+    params = make_params(TOY, rng)
+    ref = oracle_for(TOY, params, _oracle_hp(hp_kind), N, **sched)
+    op, tp = _gpu_op(TOY, params, hp_kind, N, sched)
+    for step in range(2 * N + 2):
+        grads = make_grads(TOY, sigma, 0, step)
+        info = ref.run(grads)
+        applied = op.run([torch.from_numpy(g).cuda() for g in grads])
+        assert applied == info.applied
+        st = op.stats()
+        assert st["applied"] == info.applied and np.float32(st["lr"]) == info.lr
+        clipping = hp_kind == "bert"
+        if info.applied and clipping:
+            assert abs(st["global_norm"] - float(info.global_norm)) <= 2e-6 * float(info.global_norm)
+        # bit-exact whenever the clip scale is exactly 1 on both sides
+        exact = (not clipping) or (float(info.clip_scale) == 1.0 and st["clip_scale"] == 1.0) or not info.applied
+        _compare(op, tp, ref, bitexact=exact)
+    assert op.global_step == ref.global_step
+
+
+def test_unaligned_and_missing_grads():
+    """Views at odd element offsets (4-byte aligned only) and a tensor without gradient."""
+    import gaccum_b200 as g
+    from gaccum_b200.train_op import GaccumTrainOp
+    rng = np.random.default_rng(3)
+    man = [("a/kernel", (777,)), ("a/bias", (5,)), ("b/kernel", (4097,)), ("c/kernel", (100,))]
+    params = make_params(man, rng)
+    flat = torch.zeros(1 + sum(p.size for p in params) + 16, device="cuda")
+    tp, o = [], 1                                 # start at element 1 -> pointers are 4 B aligned only
+    for p in params:
+        t = flat[o:o + p.size]; t.copy_(torch.from_numpy(p.ravel())); tp.append(t); o += p.size
+    hp = g.HParams.bert()
+    op = GaccumTrainOp(tp, [n for n, _ in man], hp, 2, lambda s: 1e-3)
+    ref = oracle_for(man, [p.ravel() for p in params], onp.HParams.bert(), 2, constant_lr=1e-3)
+    gflat = torch.zeros_like(flat)
+    for step in range(5):
+        grads = make_grads(man, 0.5, 0, step)
+        grads[3] = None
+        tg, o = [], 3                             # different misalignment for grads
+        for gr in grads:
+            if gr is None:
+                tg.append(None); continue
+            t = gflat[o:o + gr.size]; t.copy_(torch.from_numpy(gr.ravel())); tg.append(t); o += gr.size
+        info = ref.run([None if x is None else x.ravel() for x in grads])
+        op.run(tg)
+        _compare(op, tp, ref, bitexact=not info.applied)
+
+
+def test_nan_gradient_propagates():
+    """TF 1.15 clip_by_global_norm: a non-finite norm makes every update NaN."""
+    import gaccum_b200 as g
+    from gaccum_b200.train_op import GaccumTrainOp
+    man = [("w/kernel", (300,)), ("w/bias", (7,))]
+    params = make_params(man, np.random.default_rng(0))
+    tp = [torch.from_numpy(p.copy()).cuda() for p in params]
+    op = GaccumTrainOp(tp, [n for n, _ in man], g.HParams.bert(), 1, lambda s: 1e-3)
+    grads = [torch.zeros(300, device="cuda"), torch.zeros(7, device="cuda")]
+    grads[0][5] = float("nan")
+    op.run(grads)
+    assert all(torch.isnan(t).all() for t in tp)
+    assert torch.isnan(op.m_view(1)).all() and (op.accum == 0).all()
