@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -57,9 +58,12 @@ struct gaccum_plan {
   // device side
   TileDesc* d_tiles = nullptr;
   double* d_partials = nullptr;
+  float* d_tile_sumsq = nullptr;
+  uint32_t* d_tickets = nullptr;
   float* d_stats = nullptr;
   int num_sms = 0;
   int max_grid = 0;
+  uint32_t tune = 0;   // kTune* bits; GACCUM_TUNE overrides (experiments)
   std::mutex mu;
   std::map<const void*, int> grid_cache;   // kernel -> co-resident grid size
 };
@@ -145,6 +149,7 @@ static int launch_accumulate(gaccum_plan* pl, KernelParams<CAP>& prm, cudaStream
   int grid = 0;
   if (int rc = grid_for(pl, fn, &grid)) return rc;
   grid = std::max(1, std::min(grid, prm.num_tiles));
+  if (pl->tune & kTuneAccTiles) grid = std::max(1, prm.num_tiles);
   accumulate_kernel<CAP><<<grid, kThreads, 0, st>>>(prm);
   CUDA_TRY(cudaGetLastError());
   return GACCUM_OK;
@@ -160,15 +165,33 @@ static int launch_apply_inst(gaccum_plan* pl, KernelParams<CAP>& prm, cudaStream
     void* args[] = {(void*)&prm};
     CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, 0, st));
   } else {
+    if (pl->tune & kTuneAccTiles) grid = std::max(1, prm.num_tiles);
     apply_kernel<VARIANT, CLIP, HAS_G, CAP><<<grid, kThreads, 0, st>>>(prm);
     CUDA_TRY(cudaGetLastError());
   }
   return GACCUM_OK;
 }
 
+template <int VARIANT, bool HAS_G, int CAP>
+static int launch_apply_clip_dyn(gaccum_plan* pl, KernelParams<CAP>& prm, cudaStream_t st) {
+  const void* fn = (const void*)&apply_clip_kernel<VARIANT, HAS_G, CAP>;
+  int grid = 0;
+  if (int rc = grid_for(pl, fn, &grid)) return rc;
+  // one tile per WARP at a time: more CTAs than tiles/8 would only idle at the barriers
+  grid = std::max(1, std::min(grid, (prm.num_tiles + kThreads / 32 - 1) / (kThreads / 32)));
+  void* args[] = {(void*)&prm};
+  CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, 0, st));
+  return GACCUM_OK;
+}
+
 template <int CAP>
 static int launch_apply(gaccum_plan* pl, KernelParams<CAP>& prm, bool has_g, cudaStream_t st) {
   const bool clip = pl->hp.clip_norm > 0.0;
+  if (clip && !(pl->tune & kTuneStaticApply)) {
+    if (pl->hp.variant == GACCUM_ADAM)
+      return has_g ? launch_apply_clip_dyn<1, true>(pl, prm, st) : launch_apply_clip_dyn<1, false>(pl, prm, st);
+    return has_g ? launch_apply_clip_dyn<0, true>(pl, prm, st) : launch_apply_clip_dyn<0, false>(pl, prm, st);
+  }
   const int key = (pl->hp.variant == GACCUM_ADAM ? 4 : 0) | (clip ? 2 : 0) | (has_g ? 1 : 0);
   switch (key) {
     case 0: return launch_apply_inst<0, false, false>(pl, prm, st);
@@ -203,7 +226,10 @@ static void fill_common(gaccum_plan* pl, KernelParams<CAP>& prm, float* accum, f
   prm.m = m;
   prm.v = v;
   prm.partials = pl->d_partials;
+  prm.tile_sumsq = pl->d_tile_sumsq;
+  prm.tickets = pl->d_tickets;
   prm.stats = pl->d_stats;
+  prm.tune = pl->tune;
   prm.sc = sc;
 }
 
@@ -230,10 +256,11 @@ struct DeviceGuard {
 };
 
 template <int CAP>
-static int do_accumulate_tab(gaccum_plan* pl, const float* const* grads, float* accum, cudaStream_t st) {
+static int do_accumulate_tab(gaccum_plan* pl, const float* const* grads, float* accum,
+                             const gaccum_step_args* a, cudaStream_t st) {
   KernelParams<CAP>* prm = new (std::nothrow) KernelParams<CAP>();
   if (!prm) return fail(GACCUM_ENOMEM, "out of host memory");
-  fill_common(pl, *prm, accum, nullptr, nullptr, make_scalars(pl->hp, nullptr));
+  fill_common(pl, *prm, accum, nullptr, nullptr, make_scalars(pl->hp, a));
   int rc = fill_table(pl, prm->tab, grads, nullptr);
   if (rc == GACCUM_OK) rc = launch_accumulate(pl, *prm, st);
   delete prm;
@@ -350,6 +377,9 @@ int gaccum_plan_create(gaccum_plan** out, int32_t T, const int64_t* numels, cons
   if (hp->variant == GACCUM_ADAM_WEIGHT_DECAY && decay) pl->decay.assign(decay, decay + T);
   if (int rc = build_layout(pl)) { delete pl; return rc; }
   pl->device = -1;
+  // measured best on B200 so far (profiles/r01_tune_sweep.md): static round-robin beats warp tickets
+  pl->tune = kTuneKeepA | kTuneStreamState | kTuneAccTiles | kTuneStaticApply;
+  if (const char* t = getenv("GACCUM_TUNE")) pl->tune = (uint32_t)strtoul(t, nullptr, 0);
   if (device >= 0) {
     int n = gaccum_device_count();
     if (device >= n) { delete pl; return fail(GACCUM_ENODEVICE, "CUDA device %d requested but %d device(s) visible; libgaccum has no CPU fallback", device, n); }
@@ -364,10 +394,14 @@ int gaccum_plan_create(gaccum_plan** out, int32_t T, const int64_t* numels, cons
     if (e == cudaSuccess && !pl->tiles.empty())
       e = cudaMemcpy(pl->d_tiles, pl->tiles.data(), pl->tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_partials, sizeof(double) * (size_t)pl->max_grid);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_tile_sumsq, sizeof(float) * std::max<size_t>(1, pl->tiles.size()));
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_tickets, sizeof(uint32_t) * 4);
+    if (e == cudaSuccess) e = cudaMemset(pl->d_tickets, 0, sizeof(uint32_t) * 4);
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_stats, sizeof(gaccum_stats));
     if (e == cudaSuccess) e = cudaMemset(pl->d_stats, 0, sizeof(gaccum_stats));
     if (e != cudaSuccess) {
       cudaFree(pl->d_tiles); cudaFree(pl->d_partials); cudaFree(pl->d_stats);
+    cudaFree(pl->d_tile_sumsq); cudaFree(pl->d_tickets);
       delete pl;
       return fail(GACCUM_ECUDA, "plan device setup failed: %s", cudaGetErrorString(e));
     }
@@ -382,6 +416,7 @@ int gaccum_plan_destroy(gaccum_plan* pl) {
   if (pl->device >= 0) {
     DeviceGuard guard(pl->device);
     cudaFree(pl->d_tiles); cudaFree(pl->d_partials); cudaFree(pl->d_stats);
+    cudaFree(pl->d_tile_sumsq); cudaFree(pl->d_tickets);
   }
   delete pl;
   return GACCUM_OK;
@@ -404,13 +439,18 @@ int64_t gaccum_algorithmic_bytes(const gaccum_plan* pl, int32_t is_apply) {
   return pl->P * (is_apply ? 36 : 12);
 }
 
-int gaccum_accumulate(gaccum_plan* pl, const float* const* grads, float* accum, gaccum_stream_t stream) {
+static int accumulate_impl(gaccum_plan* pl, const float* const* grads, float* accum,
+                           const gaccum_step_args* a, gaccum_stream_t stream) {
   if (int rc = check_compute(pl, accum, nullptr, nullptr, false)) return rc;
   if (!grads) return fail(GACCUM_EINVAL, "grads is NULL");
   DeviceGuard guard(pl->device);
   cudaStream_t st = (cudaStream_t)stream;
-  return pl->T <= kCapSmall ? do_accumulate_tab<kCapSmall>(pl, grads, accum, st)
-                            : do_accumulate_tab<kCapLarge>(pl, grads, accum, st);
+  return pl->T <= kCapSmall ? do_accumulate_tab<kCapSmall>(pl, grads, accum, a, st)
+                            : do_accumulate_tab<kCapLarge>(pl, grads, accum, a, st);
+}
+
+int gaccum_accumulate(gaccum_plan* pl, const float* const* grads, float* accum, gaccum_stream_t stream) {
+  return accumulate_impl(pl, grads, accum, nullptr, stream);
 }
 
 int gaccum_apply(gaccum_plan* pl, const float* const* grads, float* const* params, float* accum,
@@ -429,7 +469,7 @@ int gaccum_step(gaccum_plan* pl, const float* const* grads, float* const* params
   if (int rc = check_args(a)) return rc;
   if (!grads) return fail(GACCUM_EINVAL, "grads is NULL");
   if (gaccum_is_apply_step(a->global_step, a->accum_n)) return gaccum_apply(pl, grads, params, accum, m, v, a, stream);
-  return gaccum_accumulate(pl, grads, accum, stream);
+  return accumulate_impl(pl, grads, accum, a, stream);
 }
 
 int gaccum_step_packed(gaccum_plan* pl, const float* grad_slab, float* param_slab, float* accum,

@@ -75,17 +75,43 @@ struct KernelParams {
   float* m;
   float* v;
   double* partials;   // one per CTA (apply with clip)
+  float* tile_sumsq;  // one per tile (dynamic apply): sum((a'/N)^2) of that tile
+  uint32_t* tickets;  // [0] pass-1 ticket counter, [1] pass-2 ticket counter (zero between launches)
   float* stats;       // gaccum_stats
+  uint32_t tune;      // kTune* bits (cache-policy experiments; uniform branches)
   Scalars sc;
   PtrTable<CAP> tab;
 };
 
+constexpr uint32_t kTuneKeepA = 1u;      // pass 1: a / a' lines get L2 evict_last priority
+constexpr uint32_t kTuneStreamState = 2u;  // pass 2: p, m, v (and the spent a') move with evict-first
+constexpr uint32_t kTuneAccTiles = 4u;   // accumulate: one tile per CTA (hardware scheduler) instead of persistent
+constexpr uint32_t kTuneStaticApply = 8u;  // clip-apply: static CTA round-robin (old) instead of warp tickets
+constexpr uint32_t kTuneSkipPass1 = 16u;   // TIMING EXPERIMENTS ONLY (results are wrong): skip the norm pass
+constexpr uint32_t kTuneSkipPass2 = 32u;   // TIMING EXPERIMENTS ONLY: skip the update pass
+
 // ---------------------------------------------------------------------------------------------
 // memory helpers: G is read exactly once -> streaming (evict-first) loads; zeroing the
-// accumulator is a streaming store; state uses the default policy.
+// accumulator is a streaming store.  a' must survive in L2 from pass 1 to pass 2, so it can be
+// tagged evict_last while everything that is touched once is tagged evict-first.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
 __device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ld_policy(const float4* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_policy(float4* p, const float4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
 
 template <int CAP>
 __device__ __forceinline__ const float* grad_ptr(const PtrTable<CAP>& tab, const TileDesc& d) {
@@ -182,6 +208,9 @@ template <int CAP>
 __global__ void __launch_bounds__(kThreads)
 accumulate_kernel(const __grid_constant__ KernelParams<CAP> prm) {
   int t = blockIdx.x;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    prm.stats[0] = 0.f; prm.stats[1] = prm.sc.lr; prm.stats[2] = 0.f; prm.stats[3] = 1.f;
+  }
   if (t >= prm.num_tiles) return;
   TileDesc d = prm.tiles[t];
   while (true) {
@@ -191,9 +220,6 @@ accumulate_kernel(const __grid_constant__ KernelParams<CAP> prm) {
     accumulate_tile(d, prm);
     if (tn >= prm.num_tiles) break;
     t = tn; d = dn;
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    prm.stats[0] = 0.f; prm.stats[1] = prm.sc.lr; prm.stats[2] = 0.f; prm.stats[3] = 1.f;
   }
 }
 
@@ -207,6 +233,8 @@ __device__ __forceinline__ float norm_tile(const TileDesc d, const KernelParams<
   float* __restrict__ a = prm.accum + (size_t)d.soff32 * kSlabAlign;
   const uint32_t len = d.len, tid = threadIdx.x;
   const float nf = prm.sc.nf;
+  const bool keep = (prm.tune & kTuneKeepA) != 0;
+  const uint64_t pol = policy_evict_last();
   if (g == nullptr || aligned16(g)) {
     const uint32_t nvec = len >> 2;
     const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -215,7 +243,7 @@ __device__ __forceinline__ float norm_tile(const TileDesc d, const KernelParams<
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const uint32_t i = u * kThreads + tid;
-      if (i < nvec) { va[u] = a4[i]; if (g) vg[u] = ld_stream(g4 + i); }
+      if (i < nvec) { va[u] = keep ? ld_policy(a4 + i, pol) : a4[i]; if (g) vg[u] = ld_stream(g4 + i); }
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
@@ -224,7 +252,7 @@ __device__ __forceinline__ float norm_tile(const TileDesc d, const KernelParams<
         if (g) {
           va[u].x = __fadd_rn(va[u].x, vg[u].x); va[u].y = __fadd_rn(va[u].y, vg[u].y);
           va[u].z = __fadd_rn(va[u].z, vg[u].z); va[u].w = __fadd_rn(va[u].w, vg[u].w);
-          a4[i] = va[u];
+          if (keep) st_policy(a4 + i, va[u], pol); else a4[i] = va[u];
         }
         const float nx = normalize(va[u].x, nf), ny = normalize(va[u].y, nf),
                     nz = normalize(va[u].z, nf), nw = normalize(va[u].w, nf);
@@ -280,11 +308,13 @@ __device__ __forceinline__ void update_tile(const TileDesc d, const KernelParams
     float4* v4 = reinterpret_cast<float4*>(v);
     float4* p4 = reinterpret_cast<float4*>(p);
     float4 va[kUnroll], vg[kUnroll], vp[kUnroll], vm[kUnroll], vv[kUnroll];
+    const bool strm = (prm.tune & kTuneStreamState) != 0;
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const uint32_t i = u * kThreads + tid;
       if (i < nvec) {
-        va[u] = a4[i]; vp[u] = p4[i]; vm[u] = m4[i]; vv[u] = v4[i];
+        if (strm) { va[u] = __ldcs(a4 + i); vp[u] = __ldcs(p4 + i); vm[u] = __ldcs(m4 + i); vv[u] = __ldcs(v4 + i); }
+        else { va[u] = a4[i]; vp[u] = p4[i]; vm[u] = m4[i]; vv[u] = v4[i]; }
         if (LOAD_G && g) vg[u] = ld_stream(g4 + i);
       }
     }
@@ -305,7 +335,8 @@ __device__ __forceinline__ void update_tile(const TileDesc d, const KernelParams
           e0(va[u].x, vp[u].x, vm[u].x, vv[u].x); e0(va[u].y, vp[u].y, vm[u].y, vv[u].y);
           e0(va[u].z, vp[u].z, vm[u].z, vv[u].z); e0(va[u].w, vp[u].w, vm[u].w, vv[u].w);
         }
-        p4[i] = vp[u]; m4[i] = vm[u]; v4[i] = vv[u];
+        if (strm) { __stcs(p4 + i, vp[u]); __stcs(m4 + i, vm[u]); __stcs(v4 + i, vv[u]); }
+        else { p4[i] = vp[u]; m4[i] = vm[u]; v4[i] = vv[u]; }
         __stcs(a4 + i, make_float4(0.f, 0.f, 0.f, 0.f));   // optimization.py:86-87
       }
     }
@@ -357,7 +388,7 @@ apply_kernel(const __grid_constant__ KernelParams<CAP> prm) {
     // ---- pass 1: a' = a + G (written back), sum of squares of a'/N -----------------------
     float acc = 0.f;
     int t = blockIdx.x;
-    if (t < nt) {
+    if (t < nt && !(prm.tune & kTuneSkipPass1)) {
       TileDesc d = prm.tiles[t];
       while (true) {
         const int tn = t + gridDim.x;
@@ -387,7 +418,7 @@ apply_kernel(const __grid_constant__ KernelParams<CAP> prm) {
     __syncthreads();
     s = s_bcast[0]; gn = s_bcast[1];
     // ---- pass 2, reverse order: most recently written a' lines first (L2 hits) ----------
-    if (blockIdx.x < nt) {
+    if (blockIdx.x < nt && !(prm.tune & kTuneSkipPass2)) {
       int t2 = blockIdx.x + ((nt - 1 - blockIdx.x) / gridDim.x) * gridDim.x;   // my last tile
       TileDesc d = prm.tiles[t2];
       while (true) {
@@ -416,6 +447,234 @@ apply_kernel(const __grid_constant__ KernelParams<CAP> prm) {
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     prm.stats[0] = 1.f; prm.stats[1] = prm.sc.lr; prm.stats[2] = gn; prm.stats[3] = s;
+  }
+}
+
+
+// =============================================================================================
+// apply with clipping, dynamic version: persistent WARPS pull tiles from a ticket counter.
+//
+// Static round-robin leaves ~10 % of SM time idle (SMs on the far L2 die run slower, everyone
+// waits at the grid barrier for the slowest CTA).  Here every warp owns one tile at a time and
+// fetches the next ticket with one atomicAdd whose latency hides behind the current tile, so all
+// SMs stay busy until the work is gone.  Determinism is kept by making the reduction independent
+// of who processed what: each tile's sum of squares is written to tile_sumsq[tile] (the lane ->
+// element map inside a tile is fixed), then reduced in two fixed-order levels.
+//   pass 1   tickets ascending : a' = a + G (in place, L2 evict_last), tile_sumsq[tile]
+//   barrier  ; CTA b reduces its fixed slice of tile_sumsq -> partials[b] (fp64) ; barrier
+//   all CTAs reduce partials[] in the same order -> gn, s
+//   pass 2   tickets DESCENDING: the most recently written a' tiles are consumed first (L2 hits)
+// =============================================================================================
+constexpr int kRowElems = 128;                 // one float4 per lane
+constexpr int kRowsPerTile = kTile / kRowElems;  // 16
+constexpr int kU1 = 4;                          // pass 1: rows in flight per warp (2 streams)
+constexpr int kU2 = 2;                          // pass 2: rows in flight per warp (4 streams)
+
+template <bool HAS_G, int CAP>
+__device__ __forceinline__ float norm_tile_warp(const TileDesc d, const KernelParams<CAP>& prm,
+                                                const bool keep, const uint64_t pol) {
+  const float* __restrict__ g = nullptr;
+  if constexpr (HAS_G) g = grad_ptr(prm.tab, d);
+  float* __restrict__ a = prm.accum + (size_t)d.soff32 * kSlabAlign;
+  const uint32_t len = d.len, lane = threadIdx.x & 31;
+  const float nf = prm.sc.nf;
+  float acc = 0.f;
+  if (g == nullptr || aligned16(g)) {
+    const uint32_t nvec = len >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4* a4 = reinterpret_cast<float4*>(a);
+    for (uint32_t base = 0; base < nvec; base += 32 * kU1) {
+      float4 vg[kU1], va[kU1];
+#pragma unroll
+      for (int u = 0; u < kU1; ++u) {
+        const uint32_t i = base + u * 32 + lane;
+        if (i < nvec) { va[u] = keep ? ld_policy(a4 + i, pol) : a4[i]; if (g) vg[u] = ld_stream(g4 + i); }
+      }
+#pragma unroll
+      for (int u = 0; u < kU1; ++u) {
+        const uint32_t i = base + u * 32 + lane;
+        if (i < nvec) {
+          if (g) {
+            va[u].x = __fadd_rn(va[u].x, vg[u].x); va[u].y = __fadd_rn(va[u].y, vg[u].y);
+            va[u].z = __fadd_rn(va[u].z, vg[u].z); va[u].w = __fadd_rn(va[u].w, vg[u].w);
+            if (keep) st_policy(a4 + i, va[u], pol); else a4[i] = va[u];
+          }
+          const float nx = normalize(va[u].x, nf), ny = normalize(va[u].y, nf),
+                      nz = normalize(va[u].z, nf), nw = normalize(va[u].w, nf);
+          acc = fmaf(nx, nx, acc); acc = fmaf(ny, ny, acc); acc = fmaf(nz, nz, acc); acc = fmaf(nw, nw, acc);
+        }
+      }
+    }
+    const uint32_t i = (nvec << 2) + lane;
+    if (lane < (len & 3u)) {
+      float x = a[i];
+      if (g) { x = __fadd_rn(x, ld_stream(g + i)); a[i] = x; }
+      const float n = normalize(x, nf);
+      acc = fmaf(n, n, acc);
+    }
+  } else {
+    for (uint32_t i = lane; i < len; i += 32) {
+      const float x = __fadd_rn(a[i], ld_stream(g + i));
+      a[i] = x;
+      const float n = normalize(x, nf);
+      acc = fmaf(n, n, acc);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+  return acc;
+}
+
+template <int VARIANT, int CAP>
+__device__ __forceinline__ void update_tile_warp(const TileDesc d, const KernelParams<CAP>& prm,
+                                                 const float s, const bool strm) {
+  const size_t soff = (size_t)d.soff32 * kSlabAlign;
+  float* __restrict__ a = prm.accum + soff;
+  float* __restrict__ m = prm.m + soff;
+  float* __restrict__ v = prm.v + soff;
+  float* __restrict__ p = param_ptr(prm.tab, d);
+  const bool decay = (d.tensor_flags >> 31) != 0;
+  const uint32_t len = d.len, lane = threadIdx.x & 31;
+  const Scalars& sc = prm.sc;
+  auto elem = [&](float ax, float& px, float& mx, float& vx) {
+    const float c = __fmul_rn(normalize(ax, sc.nf), s);      // optimization.py:83-84
+    adam_elem<VARIANT>(c, px, mx, vx, decay, sc);            // :85
+  };
+  if (aligned16(p)) {
+    const uint32_t nvec = len >> 2;
+    float4* a4 = reinterpret_cast<float4*>(a);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    float4* p4 = reinterpret_cast<float4*>(p);
+    for (uint32_t base = 0; base < nvec; base += 32 * kU2) {
+      float4 va[kU2], vp[kU2], vm[kU2], vv[kU2];
+#pragma unroll
+      for (int u = 0; u < kU2; ++u) {
+        const uint32_t i = base + u * 32 + lane;
+        if (i < nvec) {
+          if (strm) { va[u] = __ldcs(a4 + i); vp[u] = __ldcs(p4 + i); vm[u] = __ldcs(m4 + i); vv[u] = __ldcs(v4 + i); }
+          else { va[u] = a4[i]; vp[u] = p4[i]; vm[u] = m4[i]; vv[u] = v4[i]; }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kU2; ++u) {
+        const uint32_t i = base + u * 32 + lane;
+        if (i < nvec) {
+          elem(va[u].x, vp[u].x, vm[u].x, vv[u].x); elem(va[u].y, vp[u].y, vm[u].y, vv[u].y);
+          elem(va[u].z, vp[u].z, vm[u].z, vv[u].z); elem(va[u].w, vp[u].w, vm[u].w, vv[u].w);
+          if (strm) { __stcs(p4 + i, vp[u]); __stcs(m4 + i, vm[u]); __stcs(v4 + i, vv[u]); }
+          else { p4[i] = vp[u]; m4[i] = vm[u]; v4[i] = vv[u]; }
+          __stcs(a4 + i, make_float4(0.f, 0.f, 0.f, 0.f));   // optimization.py:86-87
+        }
+      }
+    }
+    const uint32_t i = (nvec << 2) + lane;
+    if (lane < (len & 3u)) {
+      float px = p[i], mx = m[i], vx = v[i];
+      elem(a[i], px, mx, vx);
+      p[i] = px; m[i] = mx; v[i] = vx; a[i] = 0.f;
+    }
+  } else {
+    for (uint32_t i = lane; i < len; i += 32) {
+      float px = p[i], mx = m[i], vx = v[i];
+      elem(a[i], px, mx, vx);
+      p[i] = px; m[i] = mx; v[i] = vx; a[i] = 0.f;
+    }
+  }
+}
+
+template <int VARIANT, bool HAS_G, int CAP>
+__global__ void __launch_bounds__(kThreads)
+apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
+  __shared__ double red_d[kThreads / 32];
+  __shared__ float s_bcast[2];
+  const int nt = prm.num_tiles;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool keep = (prm.tune & kTuneKeepA) != 0, strm = (prm.tune & kTuneStreamState) != 0;
+  const uint64_t pol = policy_evict_last();
+  cg::grid_group grid = cg::this_grid();
+
+  // ---- pass 1 -----------------------------------------------------------------------------
+  {
+    uint32_t raw = 0;
+    if (lane == 0) raw = atomicAdd(prm.tickets + 0, 1u);
+    int tk = (int)__shfl_sync(0xffffffffu, raw, 0);
+    if (lane == 0) raw = atomicAdd(prm.tickets + 0, 1u);
+    int tk_next = (int)__shfl_sync(0xffffffffu, raw, 0);
+    TileDesc d;
+    if (tk < nt) d = prm.tiles[tk];
+    while (tk < nt) {
+      TileDesc dn;
+      if (tk_next < nt) dn = prm.tiles[tk_next];
+      if (lane == 0) raw = atomicAdd(prm.tickets + 0, 1u);        // in flight during this tile
+      const float part = norm_tile_warp<HAS_G>(d, prm, keep, pol);
+      if (lane == 0) prm.tile_sumsq[tk] = part;
+      tk = tk_next; d = dn;
+      tk_next = (int)__shfl_sync(0xffffffffu, raw, 0);
+    }
+  }
+  grid.sync();
+  if (blockIdx.x == 0 && threadIdx.x == 0) prm.tickets[0] = 0;     // pass 1 is over everywhere
+  // ---- level 1: CTA b reduces tiles [b*L, (b+1)*L) in a fixed order ---------------------------
+  {
+    const int L = (nt + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int lo = blockIdx.x * L, hi = min(nt, lo + L);
+    double x = 0.0;
+    for (int i = lo + (int)threadIdx.x; i < hi; i += kThreads) x += (double)__ldcg(prm.tile_sumsq + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) red_d[warp] = x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) tot += red_d[w];
+      prm.partials[blockIdx.x] = tot;
+    }
+  }
+  grid.sync();
+  // ---- level 2: every CTA, same order -> bit-identical gn and s everywhere ---------------------
+  if (threadIdx.x < 32) {
+    double tot = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) tot += __ldcg(prm.partials + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (threadIdx.x == 0) {
+      const float g_norm = __fsqrt_rn((float)tot);     // tf.linalg.global_norm
+      s_bcast[0] = clip_scale(g_norm, prm.sc.clip);
+      s_bcast[1] = g_norm;
+    }
+  }
+  __syncthreads();
+  const float s = s_bcast[0], gn = s_bcast[1];
+  // ---- pass 2, descending tickets --------------------------------------------------------------
+  {
+    uint32_t raw = 0;
+    if (lane == 0) raw = atomicAdd(prm.tickets + 1, 1u);
+    int tk = (int)__shfl_sync(0xffffffffu, raw, 0);
+    if (lane == 0) raw = atomicAdd(prm.tickets + 1, 1u);
+    int tk_next = (int)__shfl_sync(0xffffffffu, raw, 0);
+    TileDesc d;
+    if (tk < nt) d = prm.tiles[nt - 1 - tk];
+    while (tk < nt) {
+      TileDesc dn;
+      if (tk_next < nt) dn = prm.tiles[nt - 1 - tk_next];
+      if (lane == 0) raw = atomicAdd(prm.tickets + 1, 1u);
+      update_tile_warp<VARIANT>(d, prm, s, strm);
+      tk = tk_next; d = dn;
+      tk_next = (int)__shfl_sync(0xffffffffu, raw, 0);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    prm.stats[0] = 1.f; prm.stats[1] = prm.sc.lr; prm.stats[2] = gn; prm.stats[3] = s;
+  }
+  // the pass-2 counter is reset by the NEXT launch's first instruction would race; instead the
+  // last CTA to finish resets it: a third ticket counts finished CTAs.
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const uint32_t done = atomicAdd(prm.tickets + 2, 1u);
+    if (done == gridDim.x - 1) { prm.tickets[1] = 0; prm.tickets[2] = 0; __threadfence(); }
   }
 }
 

@@ -56,6 +56,7 @@ class GaccumTrainOp:
         # TF1 AdamOptimizer._create_slots: beta powers start at beta
         self.beta1_power = _f32(hp.beta1)
         self.beta2_power = _f32(hp.beta2)
+        self._accum_ptr, self._m_ptr, self._v_ptr = self.accum.data_ptr(), self.m.data_ptr(), self.v.data_ptr()
         self._param_ptrs = Plan.ptr_array([p.data_ptr() for p in self.params])
         self._param_key = tuple(p.data_ptr() for p in self.params)
         self._grad_key = None
@@ -102,13 +103,28 @@ class GaccumTrainOp:
     # -- one micro-step -------------------------------------------------------------------
     def run(self, grads: Sequence[Optional[torch.Tensor]]) -> bool:
         """One ``session.run(train_op)`` (optimization.py:91-104).  Returns True if it applied."""
-        g = self.global_step
-        lr = _f32(self.lr_fn(g))
-        stream = torch.cuda.current_stream(self.device).cuda_stream
         self._refresh_param_table()
-        self.plan.step(self._grad_table(grads), self._param_ptrs, self.accum.data_ptr(), self.m.data_ptr(),
-                       self.v.data_ptr(), self._args(lr), stream)
-        applied = _lib.is_apply_step(g, self.N)
+        return self.run_bound(self._grad_table(grads))
+
+    def bind(self, grads: Sequence[Optional[torch.Tensor]]):
+        """Validate a gradient list once and return its device-pointer table.  A graph-mode caller
+        (TF hands the op raw pointers) pays nothing per step; Python callers whose gradient buffers
+        are persistent can do the same with ``run_bound(bind(grads))``."""
+        self._grad_key = None
+        table = self._grad_table(grads)
+        self._grad_key = None
+        return table
+
+    def run_bound(self, grad_table, stream: Optional[int] = None) -> bool:
+        """``run`` with a pointer table from ``bind`` (no per-step Python work over T tensors).
+        Parameters must not have been re-allocated since construction / the last ``run``."""
+        g = self.global_step
+        lr = self.lr_fn(g)
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.plan.step(grad_table, self._param_ptrs, self._accum_ptr, self._m_ptr, self._v_ptr,
+                       StepArgs(g, self.N, 0, lr, self.beta1_power, self.beta2_power, 0.0), stream)
+        applied = (g % self.N) == 0 if 0 <= g < 2**31 else _lib.is_apply_step(g, self.N)
         self._after(applied, lr)
         return applied
 

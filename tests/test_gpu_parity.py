@@ -43,13 +43,16 @@ def _oracle_hp(kind):
 
 
 def _compare(op, tp, ref, bitexact, tol=1e-5):
+    """accum is ALWAYS bit-identical (one fp32 add per micro-step, zeroed on apply); p, m, v are
+    bit-identical until the first apply whose clip scale != 1 (the norm's summation order differs
+    from the oracle's), after which they are held to the north-star tolerance."""
     worst = 0.0
     for i in range(len(tp)):
         for name, got, exp in (("p", tp[i].cpu().numpy(), ref.params[i]),
                                ("m", op.m_view(i).cpu().numpy(), ref.m[i]),
                                ("v", op.v_view(i).cpu().numpy(), ref.v[i]),
                                ("a", op.accum_view(i).cpu().numpy(), ref.accum[i])):
-            if bitexact:
+            if bitexact or name == "a":
                 assert np.array_equal(got, exp, equal_nan=True), f"tensor {i} {name} not bit-identical"
             else:
                 e = rel_err(got, exp)
@@ -72,6 +75,7 @@ def test_trajectory_matches_oracle(hp_kind, sigma, sched, N):
     params = make_params(TOY, rng)
     ref = oracle_for(TOY, params, _oracle_hp(hp_kind), N, **sched)
     op, tp = _gpu_op(TOY, params, hp_kind, N, sched)
+    exact = True
     for step in range(2 * N + 2):
         grads = make_grads(TOY, sigma, 0, step)
         info = ref.run(grads)
@@ -82,8 +86,9 @@ def test_trajectory_matches_oracle(hp_kind, sigma, sched, N):
         clipping = hp_kind == "bert"
         if info.applied and clipping:
             assert abs(st["global_norm"] - float(info.global_norm)) <= 2e-6 * float(info.global_norm)
-        # bit-exact whenever the clip scale is exactly 1 on both sides
-        exact = (not clipping) or (float(info.clip_scale) == 1.0 and st["clip_scale"] == 1.0) or not info.applied
+        # bit-exact for as long as every clip scale so far was exactly 1 on both sides
+        if info.applied and clipping and not (float(info.clip_scale) == 1.0 and st["clip_scale"] == 1.0):
+            exact = False
         _compare(op, tp, ref, bitexact=exact)
     assert op.global_step == ref.global_step
 
@@ -113,7 +118,7 @@ def test_unaligned_and_missing_grads():
             t = gflat[o:o + gr.size]; t.copy_(torch.from_numpy(gr.ravel())); tg.append(t); o += gr.size
         info = ref.run([None if x is None else x.ravel() for x in grads])
         op.run(tg)
-        _compare(op, tp, ref, bitexact=not info.applied)
+        _compare(op, tp, ref, bitexact=False)
 
 
 def test_nan_gradient_propagates():
