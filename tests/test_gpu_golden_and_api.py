@@ -1,0 +1,184 @@
+"""GPU: the CUDA path against the committed golden fixtures (reference's own optimization.py run),
+the drop-in Python API (create_optimizer & co.), the packed and host-buffer entry points."""
+import numpy as np
+import pytest
+
+import oracle_np as onp
+from common import make_grads, make_params, oracle_for, rel_err
+from golden_util import Golden, cases
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", cases())
+def test_cuda_path_reproduces_reference_fixtures(case):
+    import gaccum_b200 as g
+    from gaccum_b200.train_op import GaccumTrainOp
+    gd = Golden(case)
+    tp = [torch.from_numpy(p).cuda() for p in gd.init()]
+    op = GaccumTrainOp(tp, gd.names, g.HParams.bert(), gd.N,
+                       lambda s: g.learning_rate(gd.init_lr, gd.num_train_steps, gd.num_warmup_steps, s))
+    exact = True
+    for s in range(gd.steps):
+        applied = op.run([torch.from_numpy(x).cuda() for x in gd.grads(s)])
+        if applied and op.stats()["clip_scale"] != 1.0:
+            exact = False                      # norm summation order differs from the fixture's
+        assert op.global_step == gd.global_step(s)
+        for kind, view in (("param", lambda i: tp[i]), ("accum", op.accum_view), ("m", op.m_view), ("v", op.v_view)):
+            for i, exp in enumerate(gd.state(s, kind)):
+                got = view(i).cpu().numpy()
+                if exact or kind == "accum":
+                    assert np.array_equal(got, exp), f"{case} step {s} {kind} {gd.names[i]}"
+                else:
+                    assert np.allclose(got, exp, rtol=1e-5, atol=1e-8), f"{case} step {s} {kind} {gd.names[i]}"
+    if case == "warmup_unclipped":
+        assert exact                           # the whole trajectory was bit-identical
+
+
+def _tiny_model():
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.LayerNorm(32), torch.nn.Tanh(), torch.nn.Linear(32, 2)).cuda()
+    names = {"0.weight": "dense/kernel", "0.bias": "dense/bias", "1.weight": "LayerNorm/gamma",
+             "1.bias": "LayerNorm/beta", "3.weight": "output_weights", "3.bias": "output_bias"}
+    return m, (lambda n: names[n])
+
+
+def test_create_optimizer_drop_in_matches_oracle():
+    """create_optimizer(loss, init_lr, num_train_steps, num_warmup_steps, use_tpu) -> train_op.run()"""
+    from gaccum_b200 import graph, optimization as opt
+    graph.reset_default_graph()
+    model, rename = _tiny_model()
+    tvars = graph.register_module(model, rename)
+    xs = [torch.randn(8, 16, device="cuda") for _ in range(20)]
+    ys = [torch.randint(0, 2, (8,), device="cuda") for _ in range(20)]
+    it = {"i": 0}
+
+    def loss():
+        i = it["i"]; it["i"] += 1
+        return torch.nn.functional.cross_entropy(model(xs[i]), ys[i])
+
+    train_op = opt.create_optimizer(loss, 1e-3, 50, 4, False)
+    assert train_op.accum_n == 8 and train_op.engine.hp.clip_norm == 1.0
+    ref = onp.ReferenceTrainOp([v.tensor.detach().cpu().numpy() for v in tvars], [v.name for v in tvars],
+                               onp.HParams.bert(), 8, init_lr=1e-3, num_train_steps=50, num_warmup_steps=4)
+    assert train_op.engine.decay == ref.decay == [True, False, False, False, True, False]
+    for step in range(18):
+        grads = train_op.gradients()
+        ref.run([g.cpu().numpy() for g in grads])
+        train_op.run_with_grads(grads)
+        assert int(graph.get_global_step()) == ref.global_step == step + 1
+        for v, exp in zip(tvars, ref.params):
+            assert np.allclose(v.tensor.detach().cpu().numpy(), exp, rtol=1e-5, atol=1e-8)
+    # and the all-in-one call
+    l = train_op.run()
+    assert l is not None and torch.isfinite(l) and int(graph.get_global_step()) == 19
+
+
+def test_inline_recipe_with_tf_adam_like_example_02():
+    """distributedExample/02:47-73 -- AdamOptimizer(1e-4), N from params, no clip."""
+    from gaccum_b200 import graph, optimization as opt
+    graph.reset_default_graph()
+    man = onp.MANIFESTS["mnist_cnn"]()
+    params = make_params(man, np.random.default_rng(1))
+    tv = [graph.add_variable(n, torch.from_numpy(p.copy()).cuda()) for (n, _), p in zip(man, params)]
+    train_op = opt.gradient_accumulation_train_op(None, opt.AdamOptimizer(learning_rate=1e-4), 2)
+    ref = oracle_for(man, params, onp.HParams.tf_adam(), 2, constant_lr=1e-4)
+    for step in range(7):
+        grads = make_grads(man, 0.1, 0, step)
+        ref.run(grads)
+        train_op.run_with_grads([torch.from_numpy(x).cuda() for x in grads])
+        for v, exp in zip(tv, ref.params):
+            assert np.array_equal(v.tensor.cpu().numpy(), exp)           # no clip -> bit-exact
+    assert np.float32(train_op.engine.beta1_power) == ref.beta1_power
+    assert np.float32(train_op.engine.beta2_power) == ref.beta2_power
+
+
+def test_optimizer_apply_gradients_direct():
+    """AdamWeightDecayOptimizer.apply_gradients(zip(grads, tvars)) -- optimization.py:128-177."""
+    from gaccum_b200 import graph, optimization as opt
+    graph.reset_default_graph()
+    man = [("w/kernel", (300,)), ("w/bias", (9,)), ("skip/kernel", (5,))]
+    params = make_params(man, np.random.default_rng(2))
+    tv = [graph.add_variable(n, torch.from_numpy(p.copy()).cuda()) for (n, _), p in zip(man, params)]
+    o = opt.AdamWeightDecayOptimizer(learning_rate=0.05, weight_decay_rate=0.01, beta_1=0.9, beta_2=0.999,
+                                     epsilon=1e-6, exclude_from_weight_decay=["LayerNorm", "layer_norm", "bias"])
+    p, m, v = [x.copy() for x in params], [np.zeros_like(x) for x in params], [np.zeros_like(x) for x in params]
+    for step in range(3):
+        grads = make_grads(man, 0.2, 0, step)
+        o.apply_gradients(zip([torch.from_numpy(grads[0]).cuda(), torch.from_numpy(grads[1]).cuda(), None], tv))
+        for i in (0, 1):
+            p[i], m[i], v[i] = onp.adam_weight_decay_update(p[i], m[i], v[i], grads[i], 0.05, 0.9, 0.999, 1e-6, 0.01, i == 0)
+        for i in range(3):
+            assert np.array_equal(tv[i].tensor.cpu().numpy(), p[i])        # tensor 2 (grad None) untouched
+
+
+def test_packed_entry_point_matches_table_entry_point():
+    import gaccum_b200 as g
+    from gaccum_b200.train_op import GaccumTrainOp
+    man = [("a/kernel", (5000,)), ("a/bias", (3,)), ("LayerNorm/gamma", (70,)), ("b/kernel", (2049,))]
+    params = make_params(man, np.random.default_rng(4))
+    hp = g.HParams.bert()
+    op1 = GaccumTrainOp([torch.from_numpy(p.copy()).cuda() for p in params], [n for n, _ in man], hp, 2, lambda s: 1e-2)
+    plan = op1.plan
+    n = plan.padded_size
+    pslab = torch.zeros(n, device="cuda"); gslab = torch.zeros(n, device="cuda")
+    acc, m, v = (torch.zeros(n, device="cuda") for _ in range(3))
+    for p, o in zip(params, plan.offsets):
+        pslab[o:o + p.size] = torch.from_numpy(p)
+    for step in range(5):
+        grads = make_grads(man, 1.0, 0, step)
+        op1.run([torch.from_numpy(x).cuda() for x in grads])
+        gslab.zero_()
+        for x, o in zip(grads, plan.offsets):
+            gslab[o:o + x.size] = torch.from_numpy(x)
+        plan.step_packed(gslab.data_ptr(), pslab.data_ptr(), acc.data_ptr(), m.data_ptr(), v.data_ptr(),
+                         g.StepArgs(step, 2, 0, 1e-2, 0.9, 0.999, 0.0), -1, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        for i, o in enumerate(plan.offsets):
+            sz = params[i].size
+            assert torch.equal(pslab[o:o + sz], op1.params[i]) and torch.equal(m[o:o + sz], op1.m_view(i).ravel())
+            assert torch.equal(acc[o:o + sz], op1.accum_view(i).ravel())
+
+
+def test_host_buffer_entry_point():
+    import gaccum_b200 as g
+    from gaccum_b200.train_op import GaccumTrainOp
+    man = [("a/kernel", (40000,)), ("a/bias", (17,)), ("b/kernel", (5, 999))]
+    params = make_params(man, np.random.default_rng(6))
+    op = GaccumTrainOp([torch.from_numpy(p.copy()).cuda() for p in params], [n for n, _ in man], g.HParams.bert(), 3, lambda s: 1e-2)
+    ref = oracle_for(man, params, onp.HParams.bert(), 3, constant_lr=1e-2)
+    host_out = [torch.empty(s).pin_memory() for _, s in man]
+    for step in range(8):
+        grads = make_grads(man, 0.5, 0, step)
+        hg = [torch.from_numpy(x).pin_memory() for x in grads]
+        info = ref.run(grads)
+        applied = op.run_host(hg, host_out)
+        torch.cuda.synchronize()
+        assert applied == info.applied
+        if applied:
+            for h, exp in zip(host_out, ref.params):
+                assert rel_err(h.numpy(), exp) <= 1e-5
+        for i in range(len(man)):
+            assert np.array_equal(op.accum_view(i).cpu().numpy(), ref.accum[i])
+
+
+def test_state_dict_roundtrip_mid_window():
+    """Checkpoint under the reference's variable names (optimization.py:78,137-148), resume mid-window."""
+    import gaccum_b200 as g
+    from gaccum_b200.train_op import GaccumTrainOp
+    man = [("w/kernel", (700,)), ("w/bias", (3,))]
+    params = make_params(man, np.random.default_rng(8))
+    mk = lambda: GaccumTrainOp([torch.from_numpy(p.copy()).cuda() for p in params], [n for n, _ in man], g.HParams.bert(), 4, lambda s: 1e-2)
+    a, b = mk(), mk()
+    gr = [[torch.from_numpy(x).cuda() for x in make_grads(man, 0.3, 0, s)] for s in range(11)]
+    for s in range(6):
+        a.run(gr[s])
+    sd = a.state_dict()
+    assert "w/kernel/adam_m" in sd and "w/bias/adam_v" in sd and int(sd["global_step"]) == 6
+    b.load_state_dict(sd)
+    for s in range(6, 11):
+        a.run(gr[s]); b.run(gr[s])
+    for x, y in zip(a.params, b.params):
+        assert torch.equal(x, y)
+    assert torch.equal(a.m, b.m) and torch.equal(a.v, b.v) and torch.equal(a.accum, b.accum)
