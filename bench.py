@@ -199,23 +199,32 @@ def run_b200_arm(args):
     if args.no_clip:
         hp.clip_norm = 0.0
     sets = []
+    pgen = torch.Generator(device=dev); pgen.manual_seed(7)        # identical replicas on every rank
     for r in range(R):
-        params = [torch.randn(s, device=dev, generator=gen) * 0.02 for _, s in man]
-        op = GaccumTrainOp(params, names, hp, N, lr_fn, global_step=100001)   # steady state, mid-schedule
+        params = [torch.randn(s, device=dev, generator=pgen) * 0.02 for _, s in man]
+        dp = None
+        if world > 1 and args.dp == "fused":
+            from gaccum_b200.distributed import FusedDataParallelTrainOp
+            dp = FusedDataParallelTrainOp(params, names, hp, N, lr_fn, global_step=100001)
+            op = dp.engine
+        else:
+            op = GaccumTrainOp(params, names, hp, N, lr_fn, global_step=100001)   # steady state, mid-schedule
         op.m.normal_(0, 1e-4, generator=gen); op.v.uniform_(0, 1e-8, generator=gen)
         grads = [[torch.randn(s, device=dev, generator=gen) * args.sigma for _, s in man] for _ in range(N)]
         bound = [op.bind(gl) for gl in grads]      # what a graph-mode caller hands the op: raw pointers
-        sets.append((op, params, grads, bound))
+        sets.append((op, params, grads, bound, dp))
     P = sets[0][0].plan.num_elements
     stream = torch.cuda.current_stream(dev)
 
     cuda_stream = stream.cuda_stream
 
     def micro_step(i):
-        op, _, grads, bound = sets[i % R]
+        op, _, grads, bound, dp = sets[i % R]
         gl = grads[(i // R) % N]
         if world == 1:
             return op.run_bound(bound[(i // R) % N], cuda_stream)
+        if dp is not None:
+            return dp.run_bound(bound[(i // R) % N], cuda_stream)
         # data parallel (04:55,58 semantics with ONE reduction per window): accumulate locally,
         # all-reduce the packed slab on the apply step only, then apply without a gradient.
         if g.is_apply_step(op.global_step, N):
@@ -303,7 +312,9 @@ def run_b200_arm(args):
         "config": {"workload": f"{wl}_accum{N}", "desc": WORKLOADS[wl][2], "T": len(man), "P": P, "accum_n": N,
                    "optimizer": "tf.train.AdamOptimizer" if variant_b else "AdamWeightDecay+clip_by_global_norm(1.0)",
                    "grad_sigma": args.sigma,
-                   "parallelism": f"dp{world}" + (" nccl all-reduce of the packed accum slab on apply steps" if world > 1 else ""),
+                   "parallelism": f"dp{world}" + ("" if world == 1 else
+                                                   " fused apply kernel: reduce-scatter by NVLink peer loads + sharded update + all-gather by peer stores"
+                                                   if args.dp == "fused" else " nccl all-reduce of the packed accum slab on apply steps"),
                    "l2": f"rotating {R} independent state sets ({R * 5 * 4 * P / 1e6:.0f} MB of state+grads per rotation) > 126 MB L2",
                    "apply_launches": len(apply_ms), "accumulate_launches": len(acc_ms)},
         "roofline": {"bound": "hbm", "kernel": "apply_kernel (accumulate+/N+global-norm clip+AdamWeightDecay+zero)",
@@ -333,6 +344,7 @@ def main():
     ap.add_argument("--workload", default="bert_small", choices=sorted(WORKLOADS))
     ap.add_argument("--accum-n", type=int, default=0)
     ap.add_argument("--sigma", type=float, default=1e-3, help="gradient std; 1e-3 clips at BERT-Small, 1e-4 does not")
+    ap.add_argument("--dp", default="fused", choices=["fused", "allreduce"], help="multi-GPU exchange: in-kernel over peer memory, or NCCL all-reduce baseline")
     ap.add_argument("--no-clip", action="store_true", help="experiment: AdamWeightDecay without clip_by_global_norm (single-pass apply)")
     ap.add_argument("--e2e-steps", type=int, default=48)
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-oracle timing (0 disables)")

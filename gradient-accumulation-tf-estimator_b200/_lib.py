@@ -40,6 +40,16 @@ class StepArgs(C.Structure):
                 ("reserved2", C.c_float)]
 
 
+MAX_RANKS = 8
+DP_CTRL_BYTES = 256
+
+
+class DpComm(C.Structure):
+    """gaccum_dp_comm: peer base pointers for the fused data-parallel apply."""
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("accum_peers", C.c_void_p * MAX_RANKS),
+                ("param_peers", C.c_void_p * MAX_RANKS), ("ctrl_peers", C.c_void_p * MAX_RANKS)]
+
+
 class Stats(C.Structure):
     _fields_ = [("applied", C.c_float), ("lr", C.c_float), ("global_norm", C.c_float),
                 ("clip_scale", C.c_float)]
@@ -85,6 +95,8 @@ def _load():
         "gaccum_apply": (C.c_int, [vp, vp, vp, vp, vp, vp, C.POINTER(StepArgs), vp]),
         "gaccum_step_packed": (C.c_int, [vp, vp, vp, vp, vp, vp, C.POINTER(StepArgs), i32, vp]),
         "gaccum_read_stats": (C.c_int, [vp, vp, vp]),
+        "gaccum_dp_shard_range": (C.c_int, [vp, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]),
+        "gaccum_apply_dp": (C.c_int, [vp, C.POINTER(DpComm), vp, vp, C.POINTER(StepArgs), C.c_uint32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -176,6 +188,14 @@ class Plan:
                     force_branch: int = -1, stream: int = 0) -> None:
         _check(_load().gaccum_step_packed(self._h, grad_slab or None, param_slab or None, accum, m, v,
                                           C.byref(args), force_branch, stream))
+
+    def dp_shard_range(self, world: int, rank: int):
+        lo, hi, n = C.c_int32(), C.c_int32(), C.c_int64()
+        _check(_load().gaccum_dp_shard_range(self._h, world, rank, C.byref(lo), C.byref(hi), C.byref(n)))
+        return lo.value, hi.value, n.value
+
+    def apply_dp(self, comm: "DpComm", m: int, v: int, args: StepArgs, epoch: int, stream: int = 0) -> None:
+        _check(_load().gaccum_apply_dp(self._h, C.byref(comm), m, v, C.byref(args), epoch, stream))
 
     def read_stats(self, host_ptr: int, stream: int = 0) -> None:
         _check(_load().gaccum_read_stats(self._h, host_ptr, stream))

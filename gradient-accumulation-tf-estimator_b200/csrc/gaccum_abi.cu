@@ -17,6 +17,7 @@
 
 #include "../../include/gaccum.h"
 #include "gaccum_kernels.cuh"
+#include "gaccum_dp.cuh"
 
 using namespace gaccum;
 
@@ -61,6 +62,7 @@ struct gaccum_plan {
   float* d_tile_sumsq = nullptr;
   uint32_t* d_tickets = nullptr;
   float* d_stats = nullptr;
+  float* d_bcast = nullptr;
   int num_sms = 0;
   int max_grid = 0;
   uint32_t tune = 0;   // kTune* bits; GACCUM_TUNE overrides (experiments)
@@ -397,11 +399,12 @@ int gaccum_plan_create(gaccum_plan** out, int32_t T, const int64_t* numels, cons
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_tile_sumsq, sizeof(float) * std::max<size_t>(1, pl->tiles.size()));
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_tickets, sizeof(uint32_t) * 4);
     if (e == cudaSuccess) e = cudaMemset(pl->d_tickets, 0, sizeof(uint32_t) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_bcast, 4 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_stats, sizeof(gaccum_stats));
     if (e == cudaSuccess) e = cudaMemset(pl->d_stats, 0, sizeof(gaccum_stats));
     if (e != cudaSuccess) {
       cudaFree(pl->d_tiles); cudaFree(pl->d_partials); cudaFree(pl->d_stats);
-    cudaFree(pl->d_tile_sumsq); cudaFree(pl->d_tickets);
+    cudaFree(pl->d_tile_sumsq); cudaFree(pl->d_tickets); cudaFree(pl->d_bcast);
       delete pl;
       return fail(GACCUM_ECUDA, "plan device setup failed: %s", cudaGetErrorString(e));
     }
@@ -416,7 +419,7 @@ int gaccum_plan_destroy(gaccum_plan* pl) {
   if (pl->device >= 0) {
     DeviceGuard guard(pl->device);
     cudaFree(pl->d_tiles); cudaFree(pl->d_partials); cudaFree(pl->d_stats);
-    cudaFree(pl->d_tile_sumsq); cudaFree(pl->d_tickets);
+    cudaFree(pl->d_tile_sumsq); cudaFree(pl->d_tickets); cudaFree(pl->d_bcast);
   }
   delete pl;
   return GACCUM_OK;
@@ -491,6 +494,82 @@ int gaccum_step_packed(gaccum_plan* pl, const float* grad_slab, float* param_sla
   }
   if (!param_slab || !aligned16_host(param_slab)) return fail(GACCUM_EINVAL, "param_slab must be a 16-byte aligned device pointer");
   return launch_apply(pl, prm, grad_slab != nullptr, st);
+}
+
+static void shard_range(const gaccum_plan* pl, int world, int rank, int* lo, int* hi, int64_t* elems) {
+  // contiguous tile ranges with (nearly) equal element counts: boundary r = first tile whose
+  // cumulative element count reaches r * P / world
+  const int nt = (int)pl->tiles.size();
+  int bounds[GACCUM_MAX_RANKS + 1];
+  int64_t cum = 0;
+  int r = 1;
+  bounds[0] = 0;
+  for (int t = 0; t < nt && r < world; ++t) {
+    cum += pl->tiles[t].len;
+    while (r < world && cum >= (pl->P * r + world - 1) / world) bounds[r++] = t + 1;
+  }
+  while (r <= world) bounds[r++] = nt;
+  *lo = bounds[rank];
+  *hi = bounds[rank + 1];
+  int64_t e = 0;
+  for (int t = *lo; t < *hi; ++t) e += pl->tiles[t].len;
+  if (elems) *elems = e;
+}
+
+int gaccum_dp_shard_range(const gaccum_plan* pl, int32_t world, int32_t rank, int32_t* tile_lo,
+                          int32_t* tile_hi, int64_t* num_elements) {
+  if (!pl || !tile_lo || !tile_hi) return fail(GACCUM_EINVAL, "bad arguments to gaccum_dp_shard_range");
+  if (world < 1 || world > GACCUM_MAX_RANKS || rank < 0 || rank >= world)
+    return fail(GACCUM_EINVAL, "world must be 1..%d and 0 <= rank < world (got world=%d rank=%d)", GACCUM_MAX_RANKS, world, rank);
+  int lo, hi;
+  shard_range(pl, world, rank, &lo, &hi, num_elements);
+  *tile_lo = lo;
+  *tile_hi = hi;
+  return GACCUM_OK;
+}
+
+int gaccum_apply_dp(gaccum_plan* pl, const gaccum_dp_comm* comm, float* m, float* v,
+                    const gaccum_step_args* a, uint32_t epoch, gaccum_stream_t stream) {
+  if (!comm) return fail(GACCUM_EINVAL, "comm is NULL");
+  if (comm->world < 2 || comm->world > GACCUM_MAX_RANKS || comm->rank < 0 || comm->rank >= comm->world)
+    return fail(GACCUM_EINVAL, "world must be 2..%d and 0 <= rank < world", GACCUM_MAX_RANKS);
+  if (epoch == 0) return fail(GACCUM_EINVAL, "epoch must be non-zero");
+  if (int rc = check_args(a)) return rc;
+  if (int rc = check_compute(pl, comm->accum_peers[comm->rank], m, v, true)) return rc;
+  static_assert(kMaxRanks == GACCUM_MAX_RANKS && kCtrlBytes == GACCUM_DP_CTRL_BYTES, "header and kernel disagree");
+  DpParams prm{};
+  for (int w = 0; w < comm->world; ++w) {
+    if (!comm->accum_peers[w] || !comm->param_peers[w] || !comm->ctrl_peers[w] ||
+        !aligned16_host(comm->accum_peers[w]) || !aligned16_host(comm->param_peers[w]))
+      return fail(GACCUM_EINVAL, "peer pointers of rank %d must be non-NULL and 16-byte aligned", w);
+    prm.accum[w] = comm->accum_peers[w];
+    prm.param[w] = comm->param_peers[w];
+    prm.ctrl[w] = comm->ctrl_peers[w];
+  }
+  DeviceGuard guard(pl->device);
+  prm.tiles = pl->d_tiles;
+  prm.num_tiles = (int32_t)pl->tiles.size();
+  int lo, hi;
+  shard_range(pl, comm->world, comm->rank, &lo, &hi, nullptr);
+  prm.tile_lo = lo;
+  prm.tile_hi = hi;
+  prm.m = m;
+  prm.v = v;
+  prm.partials = pl->d_partials;
+  prm.stats = pl->d_stats;
+  prm.bcast = pl->d_bcast;
+  prm.tune = pl->tune;
+  prm.sc = make_scalars(pl->hp, a);
+  prm.rank = comm->rank;
+  prm.world = comm->world;
+  prm.epoch = epoch;
+  const void* fn = pl->hp.variant == GACCUM_ADAM ? (const void*)&dp_apply_kernel<1> : (const void*)&dp_apply_kernel<0>;
+  int grid = 0;
+  if (int rc = grid_for(pl, fn, &grid)) return rc;
+  grid = std::max(1, std::min(grid, prm.num_tiles));
+  void* args[] = {(void*)&prm};
+  CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, 0, (cudaStream_t)stream));
+  return GACCUM_OK;
 }
 
 int gaccum_read_stats(gaccum_plan* pl, gaccum_stats* host_out, gaccum_stream_t stream) {

@@ -89,6 +89,7 @@ constexpr uint32_t kTuneAccTiles = 4u;   // accumulate: one tile per CTA (hardwa
 constexpr uint32_t kTuneStaticApply = 8u;  // clip-apply: static CTA round-robin (old) instead of warp tickets
 constexpr uint32_t kTuneSkipPass1 = 16u;   // TIMING EXPERIMENTS ONLY (results are wrong): skip the norm pass
 constexpr uint32_t kTuneSkipPass2 = 32u;   // TIMING EXPERIMENTS ONLY: skip the update pass
+constexpr uint32_t kTuneSkipZero = 64u;    // TIMING EXPERIMENTS ONLY (dp kernel): skip zeroing non-owned tiles
 
 // ---------------------------------------------------------------------------------------------
 // memory helpers: G is read exactly once -> streaming (evict-first) loads; zeroing the

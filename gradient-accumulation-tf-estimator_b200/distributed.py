@@ -15,6 +15,7 @@ not reproduced.)
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -43,3 +44,122 @@ class DataParallelTrainOp:
         e.apply_only(None)                       # 04:59-66 on the summed accumulators
         e.global_step = g + 1                    # 04:74
         return True
+
+
+class FusedDataParallelTrainOp:
+    """The data-parallel train_op with the exchange INSIDE the apply kernel (csrc/gaccum_dp.cuh).
+
+    Parameters are moved into one packed slab in NVLink peer-mapped symmetric memory (the tensors
+    passed in are re-pointed at views of it, so the model keeps working unchanged); the accumulator
+    slab and a 256-byte control block live there too.  PyTorch's symmetric-memory allocator is only
+    the plumbing that maps every rank's buffers into every process -- the kernel does the
+    reduce-scatter (peer loads), the norm exchange and the all-gather (peer stores) itself.
+    Accumulate steps are rank-local: zero bytes cross NVLink until the apply step (vs one
+    all-reduce per variable per micro-step in 04:55,58,70).
+
+    m / v are sharded: each rank holds valid Adam moments only for the tiles it owns
+    (``plan.dp_shard_range``); ``gather_state()`` rebuilds full copies for checkpoints.
+    """
+
+    def __init__(self, params: Sequence[torch.Tensor], names: Sequence[str], hp, accum_n: int, lr_fn,
+                 process_group=None, exclude_from_weight_decay=("LayerNorm", "layer_norm", "bias"),
+                 global_step: int = 0):
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        from .train_op import GaccumTrainOp
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed must be initialised (backend nccl)")
+        self.group = process_group if process_group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if not (2 <= self.world <= _lib.MAX_RANKS):
+            raise ValueError(f"fused data parallelism supports 2..{_lib.MAX_RANKS} ranks of one NVLink domain")
+        dev = params[0].device
+        layout = _lib.Plan([p.numel() for p in params], None, hp, device=-1)
+        n = max(layout.padded_size, 32)
+        self.param_slab = symm.empty(n, dtype=torch.float32, device=dev)
+        self.accum_slab = symm.empty(n, dtype=torch.float32, device=dev)
+        self.ctrl = symm.empty(_lib.DP_CTRL_BYTES // 4, dtype=torch.int32, device=dev)
+        self.param_slab.zero_(); self.accum_slab.zero_(); self.ctrl.zero_()
+        views = []
+        with torch.no_grad():
+            for p, o in zip(params, layout.offsets):
+                view = self.param_slab[o:o + p.numel()].view(p.shape)
+                view.copy_(p)
+                p.data = view                      # the caller's tensors now alias the packed slab
+                views.append(p.data)
+        gname = self.group.group_name
+        self._handles = [symm.rendezvous(t, gname) for t in (self.param_slab, self.accum_slab, self.ctrl)]
+        hp_, ha_, hc_ = self._handles
+        self.comm = _lib.DpComm()
+        self.comm.rank, self.comm.world = self.rank, self.world
+        for w in range(self.world):
+            self.comm.param_peers[w] = int(hp_.buffer_ptrs[w])
+            self.comm.accum_peers[w] = int(ha_.buffer_ptrs[w])
+            self.comm.ctrl_peers[w] = int(hc_.buffer_ptrs[w])
+        if os.environ.get("GACCUM_DP_LOCAL_VA", "1") == "1":
+            # own buffers through their ordinary local mapping, not the peer-aperture alias
+            self.comm.param_peers[self.rank] = self.param_slab.data_ptr()
+            self.comm.accum_peers[self.rank] = self.accum_slab.data_ptr()
+            self.comm.ctrl_peers[self.rank] = self.ctrl.data_ptr()
+        self.peer_ptr_info = {"accum_local_va": self.accum_slab.data_ptr(), "accum_symm_va": int(ha_.buffer_ptrs[self.rank])}
+        self.engine = GaccumTrainOp(list(params), names, hp, accum_n, lr_fn, exclude_from_weight_decay,
+                                    global_step, accum=self.accum_slab)
+        self.plan = self.engine.plan
+        self.tile_lo, self.tile_hi, self.owned_elements = self.plan.dp_shard_range(self.world, self.rank)
+        self.epoch = 0
+        self.exchanges = 0
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=self.group)              # every rank's buffers are zeroed and mapped
+
+    @property
+    def global_step(self) -> int:
+        return self.engine.global_step
+
+    def run(self, grads: Sequence[Optional[torch.Tensor]]) -> bool:
+        return self.run_bound(self.engine._grad_table(grads))
+
+    def bind(self, grads):
+        return self.engine.bind(grads)
+
+    def run_bound(self, grad_table, stream: Optional[int] = None) -> bool:
+        e = self.engine
+        g = e.global_step
+        if (g % e.N) != 0:
+            return e.run_bound(grad_table, stream)
+        if stream is None:
+            stream = torch.cuda.current_stream(e.device).cuda_stream
+        from ._lib import StepArgs
+        lr = e.lr_fn(g)
+        e.plan.accumulate(grad_table, e._accum_ptr, stream)            # 04:58, rank-local
+        self.epoch += 1
+        e.plan.apply_dp(self.comm, e._m_ptr, e._v_ptr,
+                        StepArgs(g, e.N, 0, lr, e.beta1_power, e.beta2_power, 0.0), self.epoch, stream)
+        self.exchanges += 1
+        e._after(True, lr)
+        return True
+
+    def gather_state(self):
+        """Full m and v slabs (every rank's owned range all-gathered) for checkpointing."""
+        out = {}
+        for name, slab in (("m", self.engine.m), ("v", self.engine.v)):
+            full = slab.clone()
+            for w in range(self.world):
+                lo, hi, _ = self.plan.dp_shard_range(self.world, w)
+                if hi <= lo:
+                    continue
+                a = self._tile_elem_offset(lo)
+                b = self._tile_elem_offset(hi) if hi < self.plan.num_tiles else full.numel()
+                dist.broadcast(full[a:b], src=dist.get_global_rank(self.group, w), group=self.group)
+            out[name] = full
+        return out
+
+    def _tile_elem_offset(self, tile: int) -> int:
+        """Slab element offset at which tile index `tile` starts (tiles are laid out tensor by tensor)."""
+        t = 0
+        for numel, off in zip(self.plan.numels, self.plan.offsets):
+            nt = (numel + 2047) // 2048
+            if tile < t + nt:
+                return off + (tile - t) * 2048
+            t += nt
+        return self.engine.accum.numel()

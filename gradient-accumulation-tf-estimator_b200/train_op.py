@@ -28,7 +28,7 @@ class GaccumTrainOp:
     def __init__(self, params: Sequence[torch.Tensor], names: Sequence[str], hp: HParams, accum_n: int,
                  lr_fn: Callable[[int], float],
                  exclude_from_weight_decay: Optional[Sequence[str]] = ("LayerNorm", "layer_norm", "bias"),
-                 global_step: int = 0):
+                 global_step: int = 0, accum: Optional[torch.Tensor] = None):
         if len(params) != len(names):
             raise ValueError("params and names differ in length")
         if not params:
@@ -50,7 +50,12 @@ class GaccumTrainOp:
             if hp.variant == _lib.ADAM_WEIGHT_DECAY else [False] * len(params)
         self.plan = Plan([p.numel() for p in params], self.decay, hp, device=dev.index or 0)
         n = max(self.plan.padded_size, 32)
-        self.accum = torch.zeros(n, dtype=torch.float32, device=dev)
+        if accum is not None:          # caller-provided slab (e.g. NVLink peer-mapped symmetric memory)
+            if accum.numel() < n or accum.dtype != torch.float32 or accum.device != dev:
+                raise ValueError("accum must be an fp32 tensor of at least plan.padded_size elements on the params' device")
+            self.accum = accum
+        else:
+            self.accum = torch.zeros(n, dtype=torch.float32, device=dev)
         self.m = torch.zeros(n, dtype=torch.float32, device=dev)
         self.v = torch.zeros(n, dtype=torch.float32, device=dev)
         # TF1 AdamOptimizer._create_slots: beta powers start at beta

@@ -145,6 +145,37 @@ GACCUM_API int gaccum_step_packed(gaccum_plan* plan, const float* grad_slab, flo
                                   float* accum, float* m, float* v, const gaccum_step_args* args,
                                   int32_t force_branch /* -1 = from global_step, 0 = accumulate, 1 = apply */,
                                   gaccum_stream_t stream);
+/* ---- data parallel: the apply step fused with its exchange over NVLink peer memory ------- */
+/* Replaces reference distributedExample/04's MultiWorkerMirroredStrategy wiring: accumulators
+ * with aggregation=SUM (04:55) all-reduced per variable on every micro-step (04:58,70) and a
+ * replicated apply (04:59-66).  Each rank accumulates locally (gaccum_accumulate / gaccum_step)
+ * and calls gaccum_apply_dp on the apply step: ONE kernel that reduce-scatters the accumulators
+ * by peer loads, exchanges the partial global norms, updates the tiles the rank owns and
+ * all-gathers the new parameters by peer stores (csrc/gaccum_dp.cuh).  The loss is expected to be
+ * pre-divided by the number of workers, as 04:46 does. */
+#define GACCUM_MAX_RANKS 8
+#define GACCUM_DP_CTRL_BYTES 256
+typedef struct gaccum_dp_comm {
+  int32_t rank;
+  int32_t world; /* 2..GACCUM_MAX_RANKS */
+  /* Base device pointers of every rank's buffers, all mapped into this process (symmetric
+   * memory / CUDA IPC / cuMem fabric handles); entry [rank] is the local buffer.
+   *   accum_peers: packed fp32 accumulator slabs (gaccum_padded_size floats)
+   *   param_peers: packed fp32 parameter slabs, same layout (gaccum_offsets)
+   *   ctrl_peers : GACCUM_DP_CTRL_BYTES control blocks, zero-initialised once */
+  float* accum_peers[GACCUM_MAX_RANKS];
+  float* param_peers[GACCUM_MAX_RANKS];
+  uint32_t* ctrl_peers[GACCUM_MAX_RANKS];
+} gaccum_dp_comm;
+/* tiles [*tile_lo, *tile_hi) and the element count rank `rank` of `world` owns */
+GACCUM_API int gaccum_dp_shard_range(const gaccum_plan* plan, int32_t world, int32_t rank,
+                                     int32_t* tile_lo, int32_t* tile_hi, int64_t* num_elements);
+/* `epoch` must be non-zero and different from the previous call's (e.g. a call counter), and the
+ * same on every rank.  m / v: local slabs; only the owned range is read or written.
+ * All `world` ranks must call this for the same step; the call is asynchronous on `stream`. */
+GACCUM_API int gaccum_apply_dp(gaccum_plan* plan, const gaccum_dp_comm* comm, float* m, float* v,
+                               const gaccum_step_args* args, uint32_t epoch, gaccum_stream_t stream);
+
 /* Asynchronously copy the stats block of the last step to host memory (pinned for true async). */
 GACCUM_API int gaccum_read_stats(gaccum_plan* plan, gaccum_stats* host_out, gaccum_stream_t stream);
 

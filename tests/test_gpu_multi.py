@@ -59,3 +59,57 @@ def test_dp_two_gpus_identical_replicas_and_oracle_parity(tmp_path):
         ref.run([a + b for a, b in zip(_grads(0, s, world), _grads(1, s, world))])
     for i in range(len(MAN)):
         assert np.allclose(r0[f"arr_{i}"], ref.params[i], rtol=1e-5, atol=1e-7)
+
+
+def _worker_fused(rank, world, port, outdir):
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        sys.path.insert(0, p)
+    import torch.distributed as dist
+    import gaccum_b200 as g
+    from gaccum_b200.distributed import FusedDataParallelTrainOp
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    rng = np.random.default_rng(5)
+    params = [torch.from_numpy(rng.normal(0, 0.02, s).astype(np.float32)).cuda() for _, s in MAN]
+    dp = FusedDataParallelTrainOp(params, [n for n, _ in MAN], g.HParams.bert(), N, lambda s: 1e-2)
+    for s in range(STEPS):
+        dp.run([torch.from_numpy(x).cuda() for x in _grads(rank, s, world)])
+    torch.cuda.synchronize()
+    st = dp.gather_state()
+    np.savez(os.path.join(outdir, f"frank{rank}.npz"), *[p.cpu().numpy() for p in params],
+             m=st["m"].cpu().numpy(), v=st["v"].cpu().numpy(), accum=dp.engine.accum.cpu().numpy(),
+             exchanges=dp.exchanges, owned=dp.owned_elements, stats=np.array(list(dp.engine.stats().values()), dtype=np.float64))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_fused_dp_kernel_two_gpus(tmp_path):
+    """The one-kernel exchange (peer loads / peer stores) gives every rank the same parameters as the
+    single-process oracle fed the rank-summed gradient."""
+    import torch.multiprocessing as mp
+    import oracle_np as onp
+    ndev = torch.cuda.device_count()
+    world = 8 if ndev >= 8 else 4 if ndev >= 4 else 2       # W=2 -> 4 tiles/iter, W=4 -> 2, W=8 -> 1
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    mp.spawn(_worker_fused, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    rs = [np.load(tmp_path / f"frank{r}.npz") for r in range(world)]
+    r0 = rs[0]
+    T = len(MAN)
+    for r in rs[1:]:
+        for i in range(T):
+            assert np.array_equal(r0[f"arr_{i}"], r[f"arr_{i}"]), f"replicas differ in tensor {i}"
+        assert np.array_equal(r0["m"], r["m"]) and np.array_equal(r0["v"], r["v"])
+        assert np.array_equal(r0["stats"], r["stats"])                   # identical gn / clip scale
+    assert int(r0["exchanges"]) == 4
+    assert sum(int(r["owned"]) for r in rs) == sum(int(np.prod(s)) for _, s in MAN)
+    rng = np.random.default_rng(5)
+    params = [rng.normal(0, 0.02, s).astype(np.float32) for _, s in MAN]
+    ref = onp.ReferenceTrainOp(params, [n for n, _ in MAN], onp.HParams.bert(), N, constant_lr=1e-2)
+    for s in range(STEPS):
+        gs = [_grads(r, s, world) for r in range(world)]
+        ref.run([np.sum([g[i] for g in gs], axis=0, dtype=np.float32) for i in range(T)])
+    for i in range(T):
+        assert np.allclose(r0[f"arr_{i}"], ref.params[i], rtol=1e-5, atol=1e-7)
+    assert all(not r["accum"].any() for r in rs)                         # STEPS-1 is an apply step: all zero
