@@ -68,6 +68,8 @@ struct gaccum_plan {
   uint32_t tune = 0;   // kTune* bits; GACCUM_TUNE overrides (experiments)
   std::mutex mu;
   std::map<const void*, int> grid_cache;   // kernel -> co-resident grid size
+  std::map<const void*, int> stash_cache;  // kernel -> shared-memory stash tiles per CTA
+  int smem_per_sm = 0, smem_optin = 0, stash_override = -1;
 };
 
 static int build_layout(gaccum_plan* pl) {
@@ -174,26 +176,58 @@ static int launch_apply_inst(gaccum_plan* pl, KernelParams<CAP>& prm, cudaStream
   return GACCUM_OK;
 }
 
+// v2: static two-pass + shared-memory stash (+ optional ordinary launch with an atomic barrier)
 template <int VARIANT, bool HAS_G, int CAP>
-static int launch_apply_clip_dyn(gaccum_plan* pl, KernelParams<CAP>& prm, cudaStream_t st) {
-  const void* fn = (const void*)&apply_clip_kernel<VARIANT, HAS_G, CAP>;
-  int grid = 0;
-  if (int rc = grid_for(pl, fn, &grid)) return rc;
-  // one tile per WARP at a time: more CTAs than tiles/8 would only idle at the barriers
-  grid = std::max(1, std::min(grid, (prm.num_tiles + kThreads / 32 - 1) / (kThreads / 32)));
-  void* args[] = {(void*)&prm};
-  CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, 0, st));
+static int launch_apply_clip2(gaccum_plan* pl, KernelParams<CAP>& prm, cudaStream_t st) {
+  const void* fn = (const void*)&apply_clip2_kernel<VARIANT, HAS_G, CAP>;
+  int grid = 0, stash = 0;
+  {
+    std::lock_guard<std::mutex> lk(pl->mu);
+    auto it = pl->grid_cache.find(fn);
+    if (it == pl->grid_cache.end()) {
+      // keep the register-limited occupancy and give every resident CTA an equal share of shared memory
+      int per_sm = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
+      if (per_sm < 1) return fail(GACCUM_ECUDA, "kernel does not fit on an SM");
+      const int tile_bytes = kTile * (int)sizeof(float);
+      int s_tiles = (pl->smem_per_sm / per_sm - 1024 - 256) / tile_bytes;     // 1 KB driver reserve per CTA
+      s_tiles = std::max(0, std::min(s_tiles, (pl->smem_optin - 256) / tile_bytes));
+      // measured (profiles/r01_tune_sweep.md): 8 tiles/CTA is the sweet spot; 9 starves L1 of the
+      // lines it needs for in-flight loads and costs 15 %
+      s_tiles = std::min(s_tiles, pl->stash_override >= 0 ? pl->stash_override : 8);
+      CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(1, s_tiles) * tile_bytes));
+      int check = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&check, fn, kThreads, (size_t)s_tiles * tile_bytes));
+      if (check < per_sm) { s_tiles = 0; }                                   // never trade occupancy for stash
+      pl->grid_cache[fn] = std::min(per_sm * pl->num_sms, pl->max_grid);
+      pl->stash_cache[fn] = s_tiles;
+      it = pl->grid_cache.find(fn);
+    }
+    grid = it->second;
+    stash = pl->stash_cache[fn];
+  }
+  grid = std::max(1, std::min(grid, prm.num_tiles));
+  prm.stash_tiles = stash;
+  const size_t smem = (size_t)stash * kTile * sizeof(float);
+  if (pl->tune & kTuneOwnBarrier) {
+    apply_clip2_kernel<VARIANT, HAS_G, CAP><<<grid, kThreads, smem, st>>>(prm);
+    CUDA_TRY(cudaGetLastError());
+  } else {
+    void* args[] = {(void*)&prm};
+    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, smem, st));
+  }
   return GACCUM_OK;
 }
 
 template <int CAP>
 static int launch_apply(gaccum_plan* pl, KernelParams<CAP>& prm, bool has_g, cudaStream_t st) {
   const bool clip = pl->hp.clip_norm > 0.0;
-  if (clip && !(pl->tune & kTuneStaticApply)) {
+  if (clip && !(pl->tune & kTuneApplyV1)) {
     if (pl->hp.variant == GACCUM_ADAM)
-      return has_g ? launch_apply_clip_dyn<1, true>(pl, prm, st) : launch_apply_clip_dyn<1, false>(pl, prm, st);
-    return has_g ? launch_apply_clip_dyn<0, true>(pl, prm, st) : launch_apply_clip_dyn<0, false>(pl, prm, st);
+      return has_g ? launch_apply_clip2<1, true>(pl, prm, st) : launch_apply_clip2<1, false>(pl, prm, st);
+    return has_g ? launch_apply_clip2<0, true>(pl, prm, st) : launch_apply_clip2<0, false>(pl, prm, st);
   }
+
   const int key = (pl->hp.variant == GACCUM_ADAM ? 4 : 0) | (clip ? 2 : 0) | (has_g ? 1 : 0);
   switch (key) {
     case 0: return launch_apply_inst<0, false, false>(pl, prm, st);
@@ -391,6 +425,9 @@ int gaccum_plan_create(gaccum_plan** out, int32_t T, const int64_t* numels, cons
     if (e == cudaSuccess && !prop.cooperativeLaunch) e = cudaErrorNotSupported;
     const size_t tb = std::max<size_t>(1, pl->tiles.size()) * sizeof(TileDesc);
     pl->num_sms = prop.multiProcessorCount;
+    pl->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
+    pl->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (const char* t = getenv("GACCUM_STASH_TILES")) pl->stash_override = atoi(t);
     pl->max_grid = pl->num_sms * 16;
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_tiles, tb);
     if (e == cudaSuccess && !pl->tiles.empty())

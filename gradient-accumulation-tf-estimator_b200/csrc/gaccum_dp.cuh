@@ -147,8 +147,8 @@ __device__ __forceinline__ float dp_reduce_tiles(const TileDesc (&d)[TPI], const
 }
 
 template <int TPI>
-__device__ __forceinline__ float dp_pass1(const DpParams& prm, const uint64_t pol) {
-  float acc = 0.f;
+__device__ __forceinline__ double dp_pass1(const DpParams& prm, const uint64_t pol) {
+  double acc = 0.0;
   const int lo = prm.tile_lo, hi = prm.tile_hi, G = (int)gridDim.x;
   for (int t0 = lo + (int)blockIdx.x; t0 < hi; t0 += TPI * G) {
     TileDesc d[TPI];
@@ -156,7 +156,7 @@ __device__ __forceinline__ float dp_pass1(const DpParams& prm, const uint64_t po
 #pragma unroll
     for (int j = 0; j < TPI; ++j)
       if (t0 + j * G < hi) { d[j] = prm.tiles[t0 + j * G]; n = j + 1; }
-    acc = dp_reduce_tiles<TPI>(d, n, prm, acc, pol);
+    acc += (double)dp_reduce_tiles<TPI>(d, n, prm, 0.f, pol);
   }
   return acc;
 }
@@ -225,7 +225,7 @@ __device__ __forceinline__ void dp_zero_tile(const TileDesc d, const DpParams& p
 template <int VARIANT>
 __global__ void __launch_bounds__(kThreads)
 dp_apply_kernel(const __grid_constant__ DpParams prm) {
-  __shared__ float red[kThreads / 32];
+  __shared__ double red[kThreads / 32];
   __shared__ float s_bcast[2];
   cg::grid_group grid = cg::this_grid();
   const uint64_t pol = policy_evict_last();
@@ -237,7 +237,7 @@ dp_apply_kernel(const __grid_constant__ DpParams prm) {
   dp_wait(prm, 0);
 
   // ---- pass 1: reduce-scatter over peer loads + norm partial -------------------------------------
-  float acc = 0.f;
+  double acc = 0.0;
   if (!(prm.tune & kTuneSkipPass1)) {
     if (prm.world <= 2) acc = dp_pass1<4>(prm, pol);
     else if (prm.world <= 4) acc = dp_pass1<2>(prm, pol);

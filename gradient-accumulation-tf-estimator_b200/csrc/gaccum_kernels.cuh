@@ -79,6 +79,7 @@ struct KernelParams {
   uint32_t* tickets;  // [0] pass-1 ticket counter, [1] pass-2 ticket counter (zero between launches)
   float* stats;       // gaccum_stats
   uint32_t tune;      // kTune* bits (cache-policy experiments; uniform branches)
+  int32_t stash_tiles;  // apply_clip2_kernel: tiles of a' each CTA keeps in shared memory between the passes
   Scalars sc;
   PtrTable<CAP> tab;
 };
@@ -86,9 +87,11 @@ struct KernelParams {
 constexpr uint32_t kTuneKeepA = 1u;      // pass 1: a / a' lines get L2 evict_last priority
 constexpr uint32_t kTuneStreamState = 2u;  // pass 2: p, m, v (and the spent a') move with evict-first
 constexpr uint32_t kTuneAccTiles = 4u;   // accumulate: one tile per CTA (hardware scheduler) instead of persistent
-constexpr uint32_t kTuneStaticApply = 8u;  // clip-apply: static CTA round-robin (old) instead of warp tickets
+constexpr uint32_t kTuneStaticApply = 8u;  // (retired: the warp-ticket dynamic apply was slower and was removed; bit kept for sweep numbering)
 constexpr uint32_t kTuneSkipPass1 = 16u;   // TIMING EXPERIMENTS ONLY (results are wrong): skip the norm pass
 constexpr uint32_t kTuneSkipPass2 = 32u;   // TIMING EXPERIMENTS ONLY: skip the update pass
+constexpr uint32_t kTuneOwnBarrier = 128u;  // clip-apply v2: ordinary launch + atomic grid barrier (no cooperative launch)
+constexpr uint32_t kTuneApplyV1 = 256u;     // clip-apply: use the first two-pass kernel (no on-chip stash)
 constexpr uint32_t kTuneSkipZero = 64u;    // TIMING EXPERIMENTS ONLY (dp kernel): skip zeroing non-owned tiles
 
 // ---------------------------------------------------------------------------------------------
@@ -362,17 +365,19 @@ __device__ __forceinline__ void update_tile(const TileDesc d, const KernelParams
   }
 }
 
-// Deterministic CTA reduction of one float per thread -> double in thread 0.
-__device__ __forceinline__ double block_reduce_to_double(float x, float* smem /* kThreads/32 */) {
+// Deterministic CTA reduction of one double per thread -> total in thread 0.  Threads add each
+// tile's 8-element fp32 partial into an fp64 running sum, so the norm of a 335 M-element model is
+// good to ~1e-7 relative even for adversarial (constant) data.
+__device__ __forceinline__ double block_reduce_to_double(double x, double* smem /* kThreads/32 */) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) x = __fadd_rn(x, __shfl_xor_sync(0xffffffffu, x, o));
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) smem[warp] = x;
   __syncthreads();
   double tot = 0.0;
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) tot += (double)smem[w];
+    for (int w = 0; w < kThreads / 32; ++w) tot += smem[w];
   }
   return tot;
 }
@@ -380,14 +385,14 @@ __device__ __forceinline__ double block_reduce_to_double(float x, float* smem /*
 template <int VARIANT, bool CLIP, bool HAS_G, int CAP>
 __global__ void __launch_bounds__(kThreads)
 apply_kernel(const __grid_constant__ KernelParams<CAP> prm) {
-  __shared__ float red[kThreads / 32];
+  __shared__ double red[kThreads / 32];
   __shared__ float s_bcast[2];
   const int nt = prm.num_tiles;
   float s = 1.0f, gn = 0.0f;
 
   if constexpr (CLIP) {
     // ---- pass 1: a' = a + G (written back), sum of squares of a'/N -----------------------
-    float acc = 0.f;
+    double acc = 0.0;
     int t = blockIdx.x;
     if (t < nt && !(prm.tune & kTuneSkipPass1)) {
       TileDesc d = prm.tiles[t];
@@ -395,7 +400,7 @@ apply_kernel(const __grid_constant__ KernelParams<CAP> prm) {
         const int tn = t + gridDim.x;
         TileDesc dn;
         if (tn < nt) dn = prm.tiles[tn];
-        acc = norm_tile<HAS_G>(d, prm, acc);
+        acc += (double)norm_tile<HAS_G>(d, prm, 0.f);
         if (tn >= nt) break;
         t = tn; d = dn;
       }
@@ -453,93 +458,97 @@ apply_kernel(const __grid_constant__ KernelParams<CAP> prm) {
 
 
 // =============================================================================================
-// apply with clipping, dynamic version: persistent WARPS pull tiles from a ticket counter.
-//
-// Static round-robin leaves ~10 % of SM time idle (SMs on the far L2 die run slower, everyone
-// waits at the grid barrier for the slowest CTA).  Here every warp owns one tile at a time and
-// fetches the next ticket with one atomicAdd whose latency hides behind the current tile, so all
-// SMs stay busy until the work is gone.  Determinism is kept by making the reduction independent
-// of who processed what: each tile's sum of squares is written to tile_sumsq[tile] (the lane ->
-// element map inside a tile is fixed), then reduced in two fixed-order levels.
-//   pass 1   tickets ascending : a' = a + G (in place, L2 evict_last), tile_sumsq[tile]
-//   barrier  ; CTA b reduces its fixed slice of tile_sumsq -> partials[b] (fp64) ; barrier
-//   all CTAs reduce partials[] in the same order -> gn, s
-//   pass 2   tickets DESCENDING: the most recently written a' tiles are consumed first (L2 hits)
+// apply with clipping, v2: the same static two-pass schedule as apply_kernel, plus
+//   * an ON-CHIP STASH: the last `stash_tiles` tiles a CTA reduces in pass 1 never leave the SM --
+//     a' goes to shared memory instead of HBM/L2 and pass 2 (which walks the CTA's tiles in reverse)
+//     consumes it from there first.  3 CTAs x 9 tiles x 8 KB x 148 SMs = 32 MB of the 115 MB a'
+//     slab at BERT-Small; what is left competes for far fewer L2 lines.
+//   * optionally an ordinary launch with an atomic grid barrier instead of a cooperative launch
+//     (kTuneOwnBarrier): the grid never exceeds the co-resident capacity, so the barrier cannot
+//     deadlock on an otherwise idle device, and ~6 us of cooperative-launch overhead go away.
+// Thread t of a CTA reads back exactly the shared-memory words it wrote, so the stash needs no
+// synchronisation and is bank-conflict free (consecutive lanes, consecutive 16-byte words).
 // =============================================================================================
-constexpr int kRowElems = 128;                 // one float4 per lane
-constexpr int kRowsPerTile = kTile / kRowElems;  // 16
-constexpr int kU1 = 4;                          // pass 1: rows in flight per warp (2 streams)
-constexpr int kU2 = 2;                          // pass 2: rows in flight per warp (4 streams)
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void atomic_grid_barrier(uint32_t* ctr, uint32_t target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    while (ld_acquire_gpu(ctr) < target) { __nanosleep(32); }
+  }
+  __syncthreads();
+}
 
 template <bool HAS_G, int CAP>
-__device__ __forceinline__ float norm_tile_warp(const TileDesc d, const KernelParams<CAP>& prm,
-                                                const bool keep, const uint64_t pol) {
+__device__ __forceinline__ float norm_tile2(const TileDesc d, const KernelParams<CAP>& prm, float acc,
+                                            float4* __restrict__ stash, const uint64_t pol) {
   const float* __restrict__ g = nullptr;
   if constexpr (HAS_G) g = grad_ptr(prm.tab, d);
   float* __restrict__ a = prm.accum + (size_t)d.soff32 * kSlabAlign;
-  const uint32_t len = d.len, lane = threadIdx.x & 31;
+  const uint32_t len = d.len, tid = threadIdx.x;
   const float nf = prm.sc.nf;
-  float acc = 0.f;
   if (g == nullptr || aligned16(g)) {
     const uint32_t nvec = len >> 2;
     const float4* g4 = reinterpret_cast<const float4*>(g);
     float4* a4 = reinterpret_cast<float4*>(a);
-    for (uint32_t base = 0; base < nvec; base += 32 * kU1) {
-      float4 vg[kU1], va[kU1];
+    float4 vg[kUnroll], va[kUnroll];
 #pragma unroll
-      for (int u = 0; u < kU1; ++u) {
-        const uint32_t i = base + u * 32 + lane;
-        if (i < nvec) { va[u] = keep ? ld_policy(a4 + i, pol) : a4[i]; if (g) vg[u] = ld_stream(g4 + i); }
-      }
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint32_t i = u * kThreads + tid;
+      if (i < nvec) { va[u] = stash ? __ldcs(a4 + i) : ld_policy(a4 + i, pol); if (g) vg[u] = ld_stream(g4 + i); }
+    }
 #pragma unroll
-      for (int u = 0; u < kU1; ++u) {
-        const uint32_t i = base + u * 32 + lane;
-        if (i < nvec) {
-          if (g) {
-            va[u].x = __fadd_rn(va[u].x, vg[u].x); va[u].y = __fadd_rn(va[u].y, vg[u].y);
-            va[u].z = __fadd_rn(va[u].z, vg[u].z); va[u].w = __fadd_rn(va[u].w, vg[u].w);
-            if (keep) st_policy(a4 + i, va[u], pol); else a4[i] = va[u];
-          }
-          const float nx = normalize(va[u].x, nf), ny = normalize(va[u].y, nf),
-                      nz = normalize(va[u].z, nf), nw = normalize(va[u].w, nf);
-          acc = fmaf(nx, nx, acc); acc = fmaf(ny, ny, acc); acc = fmaf(nz, nz, acc); acc = fmaf(nw, nw, acc);
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint32_t i = u * kThreads + tid;
+      if (i < nvec) {
+        if (g) {
+          va[u].x = __fadd_rn(va[u].x, vg[u].x); va[u].y = __fadd_rn(va[u].y, vg[u].y);
+          va[u].z = __fadd_rn(va[u].z, vg[u].z); va[u].w = __fadd_rn(va[u].w, vg[u].w);
         }
+        if (stash) stash[i] = va[u];
+        else if (g) st_policy(a4 + i, va[u], pol);
+        const float nx = normalize(va[u].x, nf), ny = normalize(va[u].y, nf),
+                    nz = normalize(va[u].z, nf), nw = normalize(va[u].w, nf);
+        acc = fmaf(nx, nx, acc); acc = fmaf(ny, ny, acc); acc = fmaf(nz, nz, acc); acc = fmaf(nw, nw, acc);
       }
     }
-    const uint32_t i = (nvec << 2) + lane;
-    if (lane < (len & 3u)) {
+    const uint32_t i = (nvec << 2) + tid;      // < 4 tail elements always travel through global memory
+    if (i < len) {
       float x = a[i];
       if (g) { x = __fadd_rn(x, ld_stream(g + i)); a[i] = x; }
       const float n = normalize(x, nf);
       acc = fmaf(n, n, acc);
     }
   } else {
-    for (uint32_t i = lane; i < len; i += 32) {
+    for (uint32_t i = tid; i < len; i += kThreads) {
       const float x = __fadd_rn(a[i], ld_stream(g + i));
       a[i] = x;
       const float n = normalize(x, nf);
       acc = fmaf(n, n, acc);
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
   return acc;
 }
 
 template <int VARIANT, int CAP>
-__device__ __forceinline__ void update_tile_warp(const TileDesc d, const KernelParams<CAP>& prm,
-                                                 const float s, const bool strm) {
+__device__ __forceinline__ void update_tile2(const TileDesc d, const KernelParams<CAP>& prm, const float s,
+                                             const float4* __restrict__ stash) {
   const size_t soff = (size_t)d.soff32 * kSlabAlign;
   float* __restrict__ a = prm.accum + soff;
   float* __restrict__ m = prm.m + soff;
   float* __restrict__ v = prm.v + soff;
   float* __restrict__ p = param_ptr(prm.tab, d);
   const bool decay = (d.tensor_flags >> 31) != 0;
-  const uint32_t len = d.len, lane = threadIdx.x & 31;
+  const uint32_t len = d.len, tid = threadIdx.x;
   const Scalars& sc = prm.sc;
   auto elem = [&](float ax, float& px, float& mx, float& vx) {
-    const float c = __fmul_rn(normalize(ax, sc.nf), s);      // optimization.py:83-84
-    adam_elem<VARIANT>(c, px, mx, vx, decay, sc);            // :85
+    const float c = __fmul_rn(normalize(ax, sc.nf), s);     // optimization.py:83-84
+    adam_elem<VARIANT>(c, px, mx, vx, decay, sc);           // :85
   };
   if (aligned16(p)) {
     const uint32_t nvec = len >> 2;
@@ -547,36 +556,33 @@ __device__ __forceinline__ void update_tile_warp(const TileDesc d, const KernelP
     float4* m4 = reinterpret_cast<float4*>(m);
     float4* v4 = reinterpret_cast<float4*>(v);
     float4* p4 = reinterpret_cast<float4*>(p);
-    for (uint32_t base = 0; base < nvec; base += 32 * kU2) {
-      float4 va[kU2], vp[kU2], vm[kU2], vv[kU2];
+    float4 va[kUnroll], vp[kUnroll], vm[kUnroll], vv[kUnroll];
 #pragma unroll
-      for (int u = 0; u < kU2; ++u) {
-        const uint32_t i = base + u * 32 + lane;
-        if (i < nvec) {
-          if (strm) { va[u] = __ldcs(a4 + i); vp[u] = __ldcs(p4 + i); vm[u] = __ldcs(m4 + i); vv[u] = __ldcs(v4 + i); }
-          else { va[u] = a4[i]; vp[u] = p4[i]; vm[u] = m4[i]; vv[u] = v4[i]; }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < kU2; ++u) {
-        const uint32_t i = base + u * 32 + lane;
-        if (i < nvec) {
-          elem(va[u].x, vp[u].x, vm[u].x, vv[u].x); elem(va[u].y, vp[u].y, vm[u].y, vv[u].y);
-          elem(va[u].z, vp[u].z, vm[u].z, vv[u].z); elem(va[u].w, vp[u].w, vm[u].w, vv[u].w);
-          if (strm) { __stcs(p4 + i, vp[u]); __stcs(m4 + i, vm[u]); __stcs(v4 + i, vv[u]); }
-          else { p4[i] = vp[u]; m4[i] = vm[u]; v4[i] = vv[u]; }
-          __stcs(a4 + i, make_float4(0.f, 0.f, 0.f, 0.f));   // optimization.py:86-87
-        }
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint32_t i = u * kThreads + tid;
+      if (i < nvec) {
+        vp[u] = __ldcs(p4 + i); vm[u] = __ldcs(m4 + i); vv[u] = __ldcs(v4 + i);
+        va[u] = stash ? stash[i] : __ldcs(a4 + i);
       }
     }
-    const uint32_t i = (nvec << 2) + lane;
-    if (lane < (len & 3u)) {
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint32_t i = u * kThreads + tid;
+      if (i < nvec) {
+        elem(va[u].x, vp[u].x, vm[u].x, vv[u].x); elem(va[u].y, vp[u].y, vm[u].y, vv[u].y);
+        elem(va[u].z, vp[u].z, vm[u].z, vv[u].z); elem(va[u].w, vp[u].w, vm[u].w, vv[u].w);
+        __stcs(p4 + i, vp[u]); __stcs(m4 + i, vm[u]); __stcs(v4 + i, vv[u]);
+        __stcs(a4 + i, make_float4(0.f, 0.f, 0.f, 0.f));   // optimization.py:86-87
+      }
+    }
+    const uint32_t i = (nvec << 2) + tid;
+    if (i < len) {
       float px = p[i], mx = m[i], vx = v[i];
       elem(a[i], px, mx, vx);
       p[i] = px; m[i] = mx; v[i] = vx; a[i] = 0.f;
     }
   } else {
-    for (uint32_t i = lane; i < len; i += 32) {
+    for (uint32_t i = tid; i < len; i += kThreads) {
       float px = p[i], mx = m[i], vx = v[i];
       elem(a[i], px, mx, vx);
       p[i] = px; m[i] = mx; v[i] = vx; a[i] = 0.f;
@@ -584,98 +590,75 @@ __device__ __forceinline__ void update_tile_warp(const TileDesc d, const KernelP
   }
 }
 
+// a tile may be stashed only if BOTH passes will take the vector path for it
+template <bool HAS_G, int CAP>
+__device__ __forceinline__ bool stashable(const TileDesc& d, const KernelParams<CAP>& prm) {
+  bool ok = aligned16(param_ptr(prm.tab, d));
+  if constexpr (HAS_G) { const float* g = grad_ptr(prm.tab, d); ok = ok && (g == nullptr || aligned16(g)); }
+  return ok;
+}
+
 template <int VARIANT, bool HAS_G, int CAP>
 __global__ void __launch_bounds__(kThreads)
-apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
-  __shared__ double red_d[kThreads / 32];
+apply_clip2_kernel(const __grid_constant__ KernelParams<CAP> prm) {
+  extern __shared__ float4 stash_mem[];                 // stash_tiles x (kTile/4) float4
+  __shared__ double red[kThreads / 32];
   __shared__ float s_bcast[2];
-  const int nt = prm.num_tiles;
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool keep = (prm.tune & kTuneKeepA) != 0, strm = (prm.tune & kTuneStreamState) != 0;
+  const int nt = prm.num_tiles, G = (int)gridDim.x, b = (int)blockIdx.x;
+  const int my_count = b < nt ? (nt - 1 - b) / G + 1 : 0;    // tiles b, b+G, ... of this CTA
+  const int first_stashed = my_count - min(my_count, prm.stash_tiles);
   const uint64_t pol = policy_evict_last();
-  cg::grid_group grid = cg::this_grid();
+  const bool own_barrier = (prm.tune & kTuneOwnBarrier) != 0;
 
-  // ---- pass 1 -----------------------------------------------------------------------------
-  {
-    uint32_t raw = 0;
-    if (lane == 0) raw = atomicAdd(prm.tickets + 0, 1u);
-    int tk = (int)__shfl_sync(0xffffffffu, raw, 0);
-    if (lane == 0) raw = atomicAdd(prm.tickets + 0, 1u);
-    int tk_next = (int)__shfl_sync(0xffffffffu, raw, 0);
-    TileDesc d;
-    if (tk < nt) d = prm.tiles[tk];
-    while (tk < nt) {
+  // ---- pass 1 ------------------------------------------------------------------------------------
+  double acc = 0.0;
+  if (my_count > 0) {
+    TileDesc d = prm.tiles[b];
+    for (int k = 0; k < my_count; ++k) {
       TileDesc dn;
-      if (tk_next < nt) dn = prm.tiles[tk_next];
-      if (lane == 0) raw = atomicAdd(prm.tickets + 0, 1u);        // in flight during this tile
-      const float part = norm_tile_warp<HAS_G>(d, prm, keep, pol);
-      if (lane == 0) prm.tile_sumsq[tk] = part;
-      tk = tk_next; d = dn;
-      tk_next = (int)__shfl_sync(0xffffffffu, raw, 0);
+      if (k + 1 < my_count) dn = prm.tiles[b + (k + 1) * G];
+      float4* st = (k >= first_stashed && stashable<HAS_G>(d, prm)) ? stash_mem + (size_t)(k - first_stashed) * (kTile / 4) : nullptr;
+      acc += (double)norm_tile2<HAS_G>(d, prm, 0.f, st, pol);
+      d = dn;
     }
   }
-  grid.sync();
-  if (blockIdx.x == 0 && threadIdx.x == 0) prm.tickets[0] = 0;     // pass 1 is over everywhere
-  // ---- level 1: CTA b reduces tiles [b*L, (b+1)*L) in a fixed order ---------------------------
-  {
-    const int L = (nt + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int lo = blockIdx.x * L, hi = min(nt, lo + L);
-    double x = 0.0;
-    for (int i = lo + (int)threadIdx.x; i < hi; i += kThreads) x += (double)__ldcg(prm.tile_sumsq + i);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    if (lane == 0) red_d[warp] = x;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double tot = 0.0;
-#pragma unroll
-      for (int w = 0; w < kThreads / 32; ++w) tot += red_d[w];
-      prm.partials[blockIdx.x] = tot;
-    }
-  }
-  grid.sync();
-  // ---- level 2: every CTA, same order -> bit-identical gn and s everywhere ---------------------
+  const double part = block_reduce_to_double(acc, red);
+  if (threadIdx.x == 0) prm.partials[b] = part;
+  if (own_barrier) atomic_grid_barrier(prm.tickets + 3, (uint32_t)G); else cg::this_grid().sync();
+  // ---- every CTA combines the per-CTA partials in the same fixed order ---------------------------
   if (threadIdx.x < 32) {
     double tot = 0.0;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) tot += __ldcg(prm.partials + i);
+    for (int i = threadIdx.x; i < G; i += 32) tot += __ldcg(prm.partials + i);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
     if (threadIdx.x == 0) {
-      const float g_norm = __fsqrt_rn((float)tot);     // tf.linalg.global_norm
+      const float g_norm = __fsqrt_rn((float)tot);        // tf.linalg.global_norm
       s_bcast[0] = clip_scale(g_norm, prm.sc.clip);
       s_bcast[1] = g_norm;
     }
   }
   __syncthreads();
   const float s = s_bcast[0], gn = s_bcast[1];
-  // ---- pass 2, descending tickets --------------------------------------------------------------
-  {
-    uint32_t raw = 0;
-    if (lane == 0) raw = atomicAdd(prm.tickets + 1, 1u);
-    int tk = (int)__shfl_sync(0xffffffffu, raw, 0);
-    if (lane == 0) raw = atomicAdd(prm.tickets + 1, 1u);
-    int tk_next = (int)__shfl_sync(0xffffffffu, raw, 0);
-    TileDesc d;
-    if (tk < nt) d = prm.tiles[nt - 1 - tk];
-    while (tk < nt) {
+  // ---- pass 2, reverse: stash first, then the most recently written L2 lines -------------------------
+  if (my_count > 0) {
+    TileDesc d = prm.tiles[b + (my_count - 1) * G];
+    for (int k = my_count - 1; k >= 0; --k) {
       TileDesc dn;
-      if (tk_next < nt) dn = prm.tiles[nt - 1 - tk_next];
-      if (lane == 0) raw = atomicAdd(prm.tickets + 1, 1u);
-      update_tile_warp<VARIANT>(d, prm, s, strm);
-      tk = tk_next; d = dn;
-      tk_next = (int)__shfl_sync(0xffffffffu, raw, 0);
+      if (k > 0) dn = prm.tiles[b + (k - 1) * G];
+      const float4* st = (k >= first_stashed && stashable<HAS_G>(d, prm)) ? stash_mem + (size_t)(k - first_stashed) * (kTile / 4) : nullptr;
+      update_tile2<VARIANT>(d, prm, s, st);
+      d = dn;
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (b == 0 && threadIdx.x == 0) {
     prm.stats[0] = 1.f; prm.stats[1] = prm.sc.lr; prm.stats[2] = gn; prm.stats[3] = s;
   }
-  // the pass-2 counter is reset by the NEXT launch's first instruction would race; instead the
-  // last CTA to finish resets it: a third ticket counts finished CTAs.
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const uint32_t done = atomicAdd(prm.tickets + 2, 1u);
-    if (done == gridDim.x - 1) { prm.tickets[1] = 0; prm.tickets[2] = 0; __threadfence(); }
+  if (own_barrier) {          // the last CTA to leave re-arms the barrier counter for the next launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(prm.tickets + 2, 1u) == (uint32_t)G - 1) { prm.tickets[3] = 0; prm.tickets[2] = 0; __threadfence(); }
+    }
   }
 }
 
