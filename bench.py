@@ -266,34 +266,38 @@ def run_b200_arm(args):
     acc_ms = [p for p, k in zip(per, kinds) if not k]
     mean = lambda x: (sum(x) / len(x)) if x else float("nan")
 
-    # ---- e2e: host buffers through the public call (single rank only measures its own PCIe) ----
+    # ---- e2e: the C ABI's host-buffer entry point (gaccum_step_host): parameters and gradients
+    #      live in pinned HOST memory; H2D of every micro-step's gradients, D2H of the stats block
+    #      every step and of the updated parameters on apply steps are all inside the timed region ----
     e2e = None
     if args.e2e_steps > 0:
-        op, params = sets[0][0], sets[0][1]
+        from gaccum_b200.train_op import HostTrainOp
+        host_params = [(torch.randn(s) * 0.02).pin_memory() for _, s in man]
         host_grads = [[torch.randn(s).mul_(args.sigma).pin_memory() for _, s in man] for _ in range(2)]
-        host_params = [torch.empty(s).pin_memory() for _, s in man]
+        hop = HostTrainOp(host_params, names, hp, N, lr_fn, global_step=100001, device=local)
+        hb = [hop.bind(hg) for hg in host_grads]
         Ke = args.e2e_steps
-        for i in range(3):
-            op.run_host(host_grads[i % 2], host_params)
-        torch.cuda.synchronize(dev)
+        for i in range(4):
+            hop.run_bound(hb[i % 2])
+        hop.sync()
         if dist is not None:
             dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         napply = 0
-        e0.record(stream)
+        t0 = time.perf_counter()
         for i in range(Ke):
-            napply += bool(op.run_host(host_grads[i % 2], host_params))
-        e1.record(stream)
-        torch.cuda.synchronize(dev)
-        ms = e0.elapsed_time(e1)
+            napply += bool(hop.run_bound(hb[i % 2]))
+        hop.sync()
+        ms = (time.perf_counter() - t0) * 1e3        # host wall clock around enqueue + sync: the caller's view
         if dist is not None:
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         e2e = {"value": world * Ke / (ms * 1e-3), "unit": "micro-steps/s",
                "h2d_bytes_per_step": 4 * P, "d2h_bytes_per_step": int(4 * P * napply / Ke) + 16,
-               "steps": Ke, "ms_per_step": ms / Ke,
-               "note": "pinned host gradients H2D every micro-step; stats D2H every step; parameters D2H on apply steps"}
+               "steps": Ke, "ms_per_step": ms / Ke, "api": "gaccum_step_host (C ABI) via HostTrainOp.run_bound",
+               "note": "pinned host gradients H2D every micro-step; stats D2H every step; parameters D2H on apply steps; "
+                       "replicas are independent at N>1 (no exchange on this path)"}
+        del hop
 
     if rank != 0:
         if dist is not None:

@@ -95,6 +95,12 @@ def _load():
         "gaccum_apply": (C.c_int, [vp, vp, vp, vp, vp, vp, C.POINTER(StepArgs), vp]),
         "gaccum_step_packed": (C.c_int, [vp, vp, vp, vp, vp, vp, C.POINTER(StepArgs), i32, vp]),
         "gaccum_read_stats": (C.c_int, [vp, vp, vp]),
+        "gaccum_host_session_create": (C.c_int, [C.POINTER(vp), vp]),
+        "gaccum_host_session_destroy": (C.c_int, [vp]),
+        "gaccum_host_session_set_params": (C.c_int, [vp, vp]),
+        "gaccum_step_host": (C.c_int, [vp, vp, vp, C.POINTER(StepArgs), vp]),
+        "gaccum_host_session_sync": (C.c_int, [vp]),
+        "gaccum_host_session_slabs": (C.c_int, [vp, vp]),
         "gaccum_dp_shard_range": (C.c_int, [vp, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]),
         "gaccum_apply_dp": (C.c_int, [vp, C.POINTER(DpComm), vp, vp, C.POINTER(StepArgs), C.c_uint32, vp]),
     }
@@ -203,6 +209,41 @@ class Plan:
     def close(self) -> None:
         if getattr(self, "_h", None):
             _load().gaccum_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class HostSession:
+    """gaccum_host_session: the train_op for a caller whose tensors live in host memory."""
+
+    def __init__(self, plan: Plan):
+        self.plan = plan
+        h = C.c_void_p()
+        _check(_load().gaccum_host_session_create(C.byref(h), plan._h))
+        self._h = h
+
+    def set_params(self, host_ptrs) -> None:
+        _check(_load().gaccum_host_session_set_params(self._h, host_ptrs))
+
+    def step(self, host_grad_ptrs, host_param_out_ptrs, args: StepArgs, stats_ptr: int = 0) -> None:
+        _check(_load().gaccum_step_host(self._h, host_grad_ptrs, host_param_out_ptrs, C.byref(args), stats_ptr or None))
+
+    def sync(self) -> None:
+        _check(_load().gaccum_host_session_sync(self._h))
+
+    def slabs(self):
+        out = (C.c_void_p * 4)()
+        _check(_load().gaccum_host_session_slabs(self._h, out))
+        return [int(x) for x in out]
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            _load().gaccum_host_session_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -609,6 +609,143 @@ int gaccum_apply_dp(gaccum_plan* pl, const gaccum_dp_comm* comm, float* m, float
   return GACCUM_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// host-buffer session
+// ------------------------------------------------------------------------------------------
+struct gaccum_host_session {
+  gaccum_plan* plan = nullptr;
+  float *d_params = nullptr, *d_accum = nullptr, *d_m = nullptr, *d_v = nullptr;
+  float* d_stage[2] = {nullptr, nullptr};
+  cudaStream_t compute = nullptr, h2d = nullptr, d2h = nullptr;
+  cudaEvent_t buf_free[2] = {nullptr, nullptr}, h2d_done[2] = {nullptr, nullptr}, k_done = nullptr, d2h_done = nullptr;
+  uint64_t calls = 0;
+};
+
+int gaccum_host_session_destroy(gaccum_host_session* s) {
+  if (!s) return GACCUM_OK;
+  if (s->plan && s->plan->device >= 0) {
+    DeviceGuard guard(s->plan->device);
+    if (s->compute) cudaStreamSynchronize(s->compute);
+    if (s->h2d) cudaStreamSynchronize(s->h2d);
+    if (s->d2h) cudaStreamSynchronize(s->d2h);
+    cudaFree(s->d_params); cudaFree(s->d_accum); cudaFree(s->d_m); cudaFree(s->d_v);
+    cudaFree(s->d_stage[0]); cudaFree(s->d_stage[1]);
+    for (int i = 0; i < 2; ++i) { if (s->buf_free[i]) cudaEventDestroy(s->buf_free[i]); if (s->h2d_done[i]) cudaEventDestroy(s->h2d_done[i]); }
+    if (s->k_done) cudaEventDestroy(s->k_done);
+    if (s->d2h_done) cudaEventDestroy(s->d2h_done);
+    if (s->compute) cudaStreamDestroy(s->compute);
+    if (s->h2d) cudaStreamDestroy(s->h2d);
+    if (s->d2h) cudaStreamDestroy(s->d2h);
+  }
+  delete s;
+  return GACCUM_OK;
+}
+
+int gaccum_host_session_create(gaccum_host_session** out, gaccum_plan* pl) {
+  if (!out) return fail(GACCUM_EINVAL, "out is NULL");
+  *out = nullptr;
+  if (!pl) return fail(GACCUM_EINVAL, "plan is NULL");
+  if (pl->device < 0) return fail(GACCUM_ENODEVICE, "layout-only plan (device=-1): libgaccum has no CPU fallback, a CUDA device is required");
+  DeviceGuard guard(pl->device);
+  gaccum_host_session* s = new (std::nothrow) gaccum_host_session();
+  if (!s) return fail(GACCUM_ENOMEM, "out of host memory");
+  s->plan = pl;
+  const size_t bytes = (size_t)std::max<int64_t>(pl->padded, kSlabAlign) * sizeof(float);
+  cudaError_t e = cudaSuccess;
+  float** bufs[] = {&s->d_params, &s->d_accum, &s->d_m, &s->d_v, &s->d_stage[0], &s->d_stage[1]};
+  for (float** b : bufs) {
+    if (e == cudaSuccess) e = cudaMalloc(b, bytes);
+    if (e == cudaSuccess) e = cudaMemset(*b, 0, bytes);
+  }
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->compute, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->h2d, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->d2h, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&s->buf_free[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->h2d_done[i], cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->k_done, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->d2h_done, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    gaccum_host_session_destroy(s);
+    return fail(GACCUM_ECUDA, "host session setup failed: %s", cudaGetErrorString(e));
+  }
+  *out = s;
+  return GACCUM_OK;
+}
+
+int gaccum_host_session_set_params(gaccum_host_session* s, const float* const* host_params) {
+  if (!s || !host_params) return fail(GACCUM_EINVAL, "bad arguments to gaccum_host_session_set_params");
+  gaccum_plan* pl = s->plan;
+  DeviceGuard guard(pl->device);
+  for (int32_t t = 0; t < pl->T; ++t) {
+    if (pl->numel[t] == 0) continue;
+    if (!host_params[t]) return fail(GACCUM_EINVAL, "host_params[%d] is NULL", t);
+    CUDA_TRY(cudaMemcpyAsync(s->d_params + pl->offset[t], host_params[t], (size_t)pl->numel[t] * sizeof(float),
+                             cudaMemcpyHostToDevice, s->compute));
+  }
+  CUDA_TRY(cudaStreamSynchronize(s->compute));
+  return GACCUM_OK;
+}
+
+int gaccum_step_host(gaccum_host_session* s, const float* const* host_grads, float* const* host_params_out,
+                     const gaccum_step_args* a, gaccum_stats* stats_out) {
+  if (!s || !host_grads) return fail(GACCUM_EINVAL, "bad arguments to gaccum_step_host");
+  if (int rc = check_args(a)) return rc;
+  gaccum_plan* pl = s->plan;
+  DeviceGuard guard(pl->device);
+  const int b = (int)(s->calls & 1);
+  ++s->calls;
+  // H2D of this step's gradients into staging buffer b, once the kernel that last read it is done
+  CUDA_TRY(cudaStreamWaitEvent(s->h2d, s->buf_free[b], 0));
+  bool any_null = false;
+  for (int32_t t = 0; t < pl->T; ++t) {
+    if (pl->numel[t] == 0) continue;
+    if (!host_grads[t]) { any_null = true; continue; }
+    CUDA_TRY(cudaMemcpyAsync(s->d_stage[b] + pl->offset[t], host_grads[t], (size_t)pl->numel[t] * sizeof(float),
+                             cudaMemcpyHostToDevice, s->h2d));
+  }
+  if (any_null)   // tensors without a gradient contribute nothing (optimization.py:132): stage zeros
+    for (int32_t t = 0; t < pl->T; ++t)
+      if (pl->numel[t] && !host_grads[t])
+        CUDA_TRY(cudaMemsetAsync(s->d_stage[b] + pl->offset[t], 0, (size_t)pl->numel[t] * sizeof(float), s->h2d));
+  CUDA_TRY(cudaEventRecord(s->h2d_done[b], s->h2d));
+  CUDA_TRY(cudaStreamWaitEvent(s->compute, s->h2d_done[b], 0));
+  const bool apply = gaccum_is_apply_step(a->global_step, a->accum_n) != 0;
+  if (int rc = gaccum_step_packed(pl, s->d_stage[b], s->d_params, s->d_accum, s->d_m, s->d_v, a, -1, s->compute)) return rc;
+  CUDA_TRY(cudaEventRecord(s->buf_free[b], s->compute));
+  if (stats_out)
+    CUDA_TRY(cudaMemcpyAsync(stats_out, pl->d_stats, sizeof(gaccum_stats), cudaMemcpyDeviceToHost, s->compute));
+  if (apply && host_params_out) {
+    CUDA_TRY(cudaEventRecord(s->k_done, s->compute));
+    CUDA_TRY(cudaStreamWaitEvent(s->d2h, s->k_done, 0));
+    for (int32_t t = 0; t < pl->T; ++t) {
+      if (pl->numel[t] == 0 || !host_params_out[t]) continue;
+      CUDA_TRY(cudaMemcpyAsync(host_params_out[t], s->d_params + pl->offset[t], (size_t)pl->numel[t] * sizeof(float),
+                               cudaMemcpyDeviceToHost, s->d2h));
+    }
+    CUDA_TRY(cudaEventRecord(s->d2h_done, s->d2h));
+    CUDA_TRY(cudaStreamWaitEvent(s->compute, s->d2h_done, 0));   // the next apply must not overwrite params mid-copy
+  }
+  return GACCUM_OK;
+}
+
+int gaccum_host_session_sync(gaccum_host_session* s) {
+  if (!s) return fail(GACCUM_EINVAL, "session is NULL");
+  DeviceGuard guard(s->plan->device);
+  CUDA_TRY(cudaStreamSynchronize(s->h2d));
+  CUDA_TRY(cudaStreamSynchronize(s->compute));
+  CUDA_TRY(cudaStreamSynchronize(s->d2h));
+  return GACCUM_OK;
+}
+
+int gaccum_host_session_slabs(gaccum_host_session* s, float** out) {
+  if (!s || !out) return fail(GACCUM_EINVAL, "bad arguments to gaccum_host_session_slabs");
+  out[0] = s->d_params; out[1] = s->d_accum; out[2] = s->d_m; out[3] = s->d_v;
+  return GACCUM_OK;
+}
+
 int gaccum_read_stats(gaccum_plan* pl, gaccum_stats* host_out, gaccum_stream_t stream) {
   if (!pl || !host_out) return fail(GACCUM_EINVAL, "bad arguments to gaccum_read_stats");
   if (pl->device < 0) return fail(GACCUM_ENODEVICE, "layout-only plan has no stats");

@@ -244,3 +244,63 @@ class GaccumTrainOp:
         if self.hp.variant == ADAM and "beta1_power" in sd:
             self.beta1_power = float(sd["beta1_power"])
             self.beta2_power = float(sd["beta2_power"])
+
+
+class HostTrainOp:
+    """The train_op for a caller whose parameters and gradients live in HOST memory (the reference's
+    CPU placement, distributedExample/02 "1 worker CPU").  A thin state holder over the C ABI's
+    ``gaccum_host_session``: gradients go H2D every micro-step (double-buffered), the kernel runs,
+    updated parameters come back D2H on apply steps, the 16-byte stats block every step.
+    ``host_params`` are updated in place; pin them (and the gradients) for asynchronous copies."""
+
+    def __init__(self, host_params: Sequence[torch.Tensor], names: Sequence[str], hp: HParams, accum_n: int,
+                 lr_fn: Callable[[int], float],
+                 exclude_from_weight_decay: Optional[Sequence[str]] = ("LayerNorm", "layer_norm", "bias"),
+                 global_step: int = 0, device: int = 0):
+        for p in host_params:
+            if p.device.type != "cpu" or p.dtype != torch.float32 or not p.is_contiguous():
+                raise ValueError("host_params must be contiguous fp32 CPU tensors")
+        self.host_params = list(host_params)
+        self.names, self.hp, self.N, self.lr_fn = list(names), hp, int(accum_n), lr_fn
+        self.global_step = int(global_step)
+        self.decay = _lib.decay_mask(self.names, hp.weight_decay_rate, exclude_from_weight_decay) \
+            if hp.variant == _lib.ADAM_WEIGHT_DECAY else [False] * len(host_params)
+        self.plan = Plan([p.numel() for p in host_params], self.decay, hp, device=device)
+        self.session = _lib.HostSession(self.plan)
+        self._param_ptrs = Plan.ptr_array([p.data_ptr() for p in self.host_params])
+        self.session.set_params(self._param_ptrs)
+        self.beta1_power, self.beta2_power = _f32(hp.beta1), _f32(hp.beta2)
+        self.stats_host = torch.zeros(4, dtype=torch.float32)
+        try:
+            self.stats_host = self.stats_host.pin_memory()
+        except Exception:
+            pass
+
+    def bind(self, host_grads: Sequence[Optional[torch.Tensor]]):
+        for g, p in zip(host_grads, self.host_params):
+            if g is not None and (g.device.type != "cpu" or g.dtype != torch.float32 or not g.is_contiguous() or g.numel() != p.numel()):
+                raise ValueError("host gradients must be contiguous fp32 CPU tensors shaped like their parameter")
+        return Plan.ptr_array([0 if g is None else g.data_ptr() for g in host_grads])
+
+    def run(self, host_grads: Sequence[Optional[torch.Tensor]]) -> bool:
+        return self.run_bound(self.bind(host_grads))
+
+    def run_bound(self, grad_ptrs) -> bool:
+        g = self.global_step
+        lr = self.lr_fn(g)
+        self.session.step(grad_ptrs, self._param_ptrs, StepArgs(g, self.N, 0, lr, self.beta1_power, self.beta2_power, 0.0),
+                          self.stats_host.data_ptr())
+        applied = _lib.is_apply_step(g, self.N)
+        if applied and self.hp.variant == ADAM:
+            self.beta1_power = _f32(np.float32(self.beta1_power) * np.float32(self.hp.beta1))
+            self.beta2_power = _f32(np.float32(self.beta2_power) * np.float32(self.hp.beta2))
+        self.global_step = g + 1
+        return applied
+
+    def sync(self) -> None:
+        self.session.sync()
+
+    def stats(self) -> Dict[str, float]:
+        self.sync()
+        a, lr, gn, s = self.stats_host.tolist()
+        return {"applied": bool(a), "lr": lr, "global_norm": gn, "clip_scale": s}

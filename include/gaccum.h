@@ -176,6 +176,27 @@ GACCUM_API int gaccum_dp_shard_range(const gaccum_plan* plan, int32_t world, int
 GACCUM_API int gaccum_apply_dp(gaccum_plan* plan, const gaccum_dp_comm* comm, float* m, float* v,
                                const gaccum_step_args* args, uint32_t epoch, gaccum_stream_t stream);
 
+/* ---- host-buffer session: the same train_op for a caller whose tensors live in HOST memory -- */
+/* (e.g. the reference run with CPU placement, distributedExample/02 "1 worker CPU").  The session
+ * keeps params / accum / m / v resident in HBM in packed layout; every micro-step copies that
+ * step's gradients host->device (double-buffered on a private copy stream so the copy of step k+1
+ * overlaps the kernel of step k), launches the one kernel, and on apply steps copies the updated
+ * parameters device->host.  Pinned host memory makes the copies truly asynchronous.
+ * gaccum_step_host returns after enqueueing; gaccum_host_session_sync waits for completion. */
+typedef struct gaccum_host_session gaccum_host_session;
+GACCUM_API int gaccum_host_session_create(gaccum_host_session** out, gaccum_plan* plan);
+GACCUM_API int gaccum_host_session_destroy(gaccum_host_session* s);
+/* initial values of the trainable variables (optimization.py:70) -> HBM; synchronous */
+GACCUM_API int gaccum_host_session_set_params(gaccum_host_session* s, const float* const* host_params);
+/* host_grads[i] may be NULL (no gradient).  host_params_out (may be NULL) receives the updated
+ * parameters on apply steps.  stats_out (may be NULL) receives the stats block every step. */
+GACCUM_API int gaccum_step_host(gaccum_host_session* s, const float* const* host_grads,
+                                float* const* host_params_out, const gaccum_step_args* args,
+                                gaccum_stats* stats_out);
+GACCUM_API int gaccum_host_session_sync(gaccum_host_session* s);
+/* device pointers of the resident slabs (params, accum, m, v) for inspection: out[4] */
+GACCUM_API int gaccum_host_session_slabs(gaccum_host_session* s, float** out);
+
 /* Asynchronously copy the stats block of the last step to host memory (pinned for true async). */
 GACCUM_API int gaccum_read_stats(gaccum_plan* plan, gaccum_stats* host_out, gaccum_stream_t stream);
 
