@@ -139,19 +139,30 @@ class TrainOp:
     """The object ``create_optimizer`` returns; ``run()`` == ``session.run(train_op)``."""
 
     def __init__(self, loss: LossLike, tvars: Sequence[graph.Variable], optimizer: _OptimizerBase,
-                 accum_n: int, clip: Optional[float], global_step: graph.GlobalStep, process_group=None):
+                 accum_n: int, clip: Optional[float], global_step: graph.GlobalStep, process_group=None,
+                 dp_mode: str = "fused"):
         self.loss = loss
         self.tvars = list(tvars)
         self.optimizer = optimizer
         self.global_step = global_step
-        self.engine = GaccumTrainOp([v.tensor for v in self.tvars], [v.name for v in self.tvars],
-                                    optimizer._hparams(clip or 0.0), accum_n, _lr_callable(optimizer.learning_rate),
-                                    exclude_from_weight_decay=getattr(optimizer, "exclude_from_weight_decay", None),
-                                    global_step=int(global_step))
+        tensors, names = [v.tensor for v in self.tvars], [v.name for v in self.tvars]
+        hp = optimizer._hparams(clip or 0.0)
+        lr_fn = _lr_callable(optimizer.learning_rate)
+        exclude = getattr(optimizer, "exclude_from_weight_decay", None)
         self.dp = None
         if process_group is not None:
-            from .distributed import DataParallelTrainOp
-            self.dp = DataParallelTrainOp(self.engine, process_group)
+            # reference 04: MultiWorkerMirroredStrategy.  "fused": the exchange happens inside the apply
+            # kernel over NVLink peer memory; "allreduce": NCCL all-reduce of the slab + replicated apply.
+            from .distributed import DataParallelTrainOp, FusedDataParallelTrainOp
+            pg = None if process_group is True else process_group
+            if dp_mode == "fused":
+                self.dp = FusedDataParallelTrainOp(tensors, names, hp, accum_n, lr_fn, pg, exclude, int(global_step))
+                self.engine = self.dp.engine
+            else:
+                self.engine = GaccumTrainOp(tensors, names, hp, accum_n, lr_fn, exclude, int(global_step))
+                self.dp = DataParallelTrainOp(self.engine, pg)
+        else:
+            self.engine = GaccumTrainOp(tensors, names, hp, accum_n, lr_fn, exclude, int(global_step))
         self.last_loss: Optional[torch.Tensor] = None
 
     @property
@@ -180,14 +191,15 @@ class TrainOp:
 
 def gradient_accumulation_train_op(loss: LossLike, optimizer: _OptimizerBase, gradient_accumulation_multiplier: int,
                                    clip_norm: Optional[float] = None, global_step: Optional[graph.GlobalStep] = None,
-                                   tvars: Optional[Sequence[graph.Variable]] = None, process_group=None) -> TrainOp:
+                                   tvars: Optional[Sequence[graph.Variable]] = None, process_group=None,
+                                   dp_mode: str = "fused") -> TrainOp:
     """The recipe the example scripts inline (02:47-73, 04:48-74, another-example.py:126-155):
     N from ``params``, optimizer given, no clipping unless asked."""
     gs = global_step or graph.get_or_create_global_step()
     tv = list(tvars) if tvars is not None else graph.trainable_variables()
     if not tv:
         raise ValueError("no trainable variables registered (graph.add_variable / graph.register_module)")
-    return TrainOp(loss, tv, optimizer, int(gradient_accumulation_multiplier), clip_norm, gs, process_group)
+    return TrainOp(loss, tv, optimizer, int(gradient_accumulation_multiplier), clip_norm, gs, process_group, dp_mode)
 
 
 def create_optimizer(loss, init_lr, num_train_steps, num_warmup_steps, use_tpu):
