@@ -177,27 +177,29 @@ static int launch_apply_inst(gaccum_plan* pl, KernelParams<CAP>& prm, cudaStream
 }
 
 // v2: static two-pass + shared-memory stash (+ optional ordinary launch with an atomic barrier)
-template <int VARIANT, bool HAS_G, int CAP>
-static int launch_apply_clip2(gaccum_plan* pl, KernelParams<CAP>& prm, cudaStream_t st) {
-  const void* fn = (const void*)&apply_clip2_kernel<VARIANT, HAS_G, CAP>;
+template <int VARIANT, bool HAS_G, int CAP, bool USE_TMEM>
+static int launch_apply_clip2_t(gaccum_plan* pl, KernelParams<CAP>& prm, cudaStream_t st) {
+  const void* fn = (const void*)&apply_clip2_kernel<VARIANT, HAS_G, CAP, USE_TMEM>;
   int grid = 0, stash = 0;
   {
     std::lock_guard<std::mutex> lk(pl->mu);
     auto it = pl->grid_cache.find(fn);
     if (it == pl->grid_cache.end()) {
       // keep the register-limited occupancy and give every resident CTA an equal share of shared memory
+      constexpr int kGroups = USE_TMEM ? kGroups3 : 1;
+      constexpr int kBlock = kThreads * kGroups;
       int per_sm = 0;
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlock, 0));
       if (per_sm < 1) return fail(GACCUM_ECUDA, "kernel does not fit on an SM");
-      const int tile_bytes = kTile * (int)sizeof(float);
-      int s_tiles = (pl->smem_per_sm / per_sm - 1024 - 256) / tile_bytes;     // 1 KB driver reserve per CTA
-      s_tiles = std::max(0, std::min(s_tiles, (pl->smem_optin - 256) / tile_bytes));
+      const int tile_bytes = kTile * (int)sizeof(float) * kGroups;          // every group gets its own stash
+      int s_tiles = (pl->smem_per_sm / per_sm - 1024 - 512) / tile_bytes;     // 1 KB driver reserve per CTA
+      s_tiles = std::max(0, std::min(s_tiles, (pl->smem_optin - 512) / tile_bytes));
       // measured (profiles/r01_tune_sweep.md): 8 tiles/CTA is the sweet spot; 9 starves L1 of the
       // lines it needs for in-flight loads and costs 15 %
       s_tiles = std::min(s_tiles, pl->stash_override >= 0 ? pl->stash_override : 8);
       CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(1, s_tiles) * tile_bytes));
       int check = 0;
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&check, fn, kThreads, (size_t)s_tiles * tile_bytes));
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&check, fn, kBlock, (size_t)s_tiles * tile_bytes));
       if (check < per_sm) { s_tiles = 0; }                                   // never trade occupancy for stash
       pl->grid_cache[fn] = std::min(per_sm * pl->num_sms, pl->max_grid);
       pl->stash_cache[fn] = s_tiles;
@@ -206,17 +208,25 @@ static int launch_apply_clip2(gaccum_plan* pl, KernelParams<CAP>& prm, cudaStrea
     grid = it->second;
     stash = pl->stash_cache[fn];
   }
-  grid = std::max(1, std::min(grid, prm.num_tiles));
+  constexpr int kGroupsL = USE_TMEM ? kGroups3 : 1;
+  grid = std::max(1, std::min(grid, (prm.num_tiles + kGroupsL - 1) / kGroupsL));
   prm.stash_tiles = stash;
-  const size_t smem = (size_t)stash * kTile * sizeof(float);
+  prm.tmem_tiles = USE_TMEM ? kTmemTiles : 0;
+  const size_t smem = (size_t)stash * kTile * sizeof(float) * kGroupsL;
   if (pl->tune & kTuneOwnBarrier) {
-    apply_clip2_kernel<VARIANT, HAS_G, CAP><<<grid, kThreads, smem, st>>>(prm);
+    apply_clip2_kernel<VARIANT, HAS_G, CAP, USE_TMEM><<<grid, kThreads * kGroupsL, smem, st>>>(prm);
     CUDA_TRY(cudaGetLastError());
   } else {
     void* args[] = {(void*)&prm};
-    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, smem, st));
+    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads * kGroupsL), args, smem, st));
   }
   return GACCUM_OK;
+}
+
+template <int VARIANT, bool HAS_G, int CAP>
+static int launch_apply_clip2(gaccum_plan* pl, KernelParams<CAP>& prm, cudaStream_t st) {
+  return (pl->tune & kTuneTmemStash) ? launch_apply_clip2_t<VARIANT, HAS_G, CAP, true>(pl, prm, st)
+                                     : launch_apply_clip2_t<VARIANT, HAS_G, CAP, false>(pl, prm, st);
 }
 
 template <int CAP>
@@ -413,9 +423,15 @@ int gaccum_plan_create(gaccum_plan** out, int32_t T, const int64_t* numels, cons
   if (hp->variant == GACCUM_ADAM_WEIGHT_DECAY && decay) pl->decay.assign(decay, decay + T);
   if (int rc = build_layout(pl)) { delete pl; return rc; }
   pl->device = -1;
-  // measured best on B200 so far (profiles/r01_tune_sweep.md): static round-robin beats warp tickets
-  pl->tune = kTuneKeepA | kTuneStreamState | kTuneAccTiles | kTuneStaticApply;
+  // measured best on B200 (profiles/r01_tune_sweep.md): evict_last a', streaming state, tile-per-CTA
+  // accumulate, shared-memory + Tensor-Memory stash of a'.  GACCUM_TUNE overrides for A/B sweeps; the
+  // bits that skip work (timing decomposition, WRONG results) additionally need GACCUM_EXPERIMENTS=1.
+  pl->tune = kTuneKeepA | kTuneStreamState | kTuneAccTiles | kTuneStaticApply | kTuneTmemStash;
   if (const char* t = getenv("GACCUM_TUNE")) pl->tune = (uint32_t)strtoul(t, nullptr, 0);
+  if ((pl->tune & (kTuneSkipPass1 | kTuneSkipPass2 | kTuneSkipZero)) && !getenv("GACCUM_EXPERIMENTS")) {
+    delete pl;
+    return fail(GACCUM_EINVAL, "GACCUM_TUNE requests a timing experiment that produces wrong results; set GACCUM_EXPERIMENTS=1 to allow it");
+  }
   if (device >= 0) {
     int n = gaccum_device_count();
     if (device >= n) { delete pl; return fail(GACCUM_ENODEVICE, "CUDA device %d requested but %d device(s) visible; libgaccum has no CPU fallback", device, n); }

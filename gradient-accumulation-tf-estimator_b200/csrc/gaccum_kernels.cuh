@@ -80,6 +80,7 @@ struct KernelParams {
   float* stats;       // gaccum_stats
   uint32_t tune;      // kTune* bits (cache-policy experiments; uniform branches)
   int32_t stash_tiles;  // apply_clip2_kernel: tiles of a' each CTA keeps in shared memory between the passes
+  int32_t tmem_tiles;   // ... and in Tensor Memory (0 or kTmemTiles)
   Scalars sc;
   PtrTable<CAP> tab;
 };
@@ -92,6 +93,7 @@ constexpr uint32_t kTuneSkipPass1 = 16u;   // TIMING EXPERIMENTS ONLY (results a
 constexpr uint32_t kTuneSkipPass2 = 32u;   // TIMING EXPERIMENTS ONLY: skip the update pass
 constexpr uint32_t kTuneOwnBarrier = 128u;  // clip-apply v2: ordinary launch + atomic grid barrier (no cooperative launch)
 constexpr uint32_t kTuneApplyV1 = 256u;     // clip-apply: use the first two-pass kernel (no on-chip stash)
+constexpr uint32_t kTuneTmemStash = 512u;   // clip-apply v2: also park a' tiles in Tensor Memory (tcgen05.st / tcgen05.ld)
 constexpr uint32_t kTuneSkipZero = 64u;    // TIMING EXPERIMENTS ONLY (dp kernel): skip zeroing non-owned tiles
 
 // ---------------------------------------------------------------------------------------------
@@ -368,7 +370,7 @@ __device__ __forceinline__ void update_tile(const TileDesc d, const KernelParams
 // Deterministic CTA reduction of one double per thread -> total in thread 0.  Threads add each
 // tile's 8-element fp32 partial into an fp64 running sum, so the norm of a 335 M-element model is
 // good to ~1e-7 relative even for adversarial (constant) data.
-__device__ __forceinline__ double block_reduce_to_double(double x, double* smem /* kThreads/32 */) {
+__device__ __forceinline__ double block_reduce_to_double(double x, double* smem /* blockDim.x/32 */) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -376,8 +378,8 @@ __device__ __forceinline__ double block_reduce_to_double(double x, double* smem 
   __syncthreads();
   double tot = 0.0;
   if (threadIdx.x == 0) {
-#pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) tot += smem[w];
+    const int nw = (int)blockDim.x >> 5;
+    for (int w = 0; w < nw; ++w) tot += smem[w];
   }
   return tot;
 }
@@ -459,9 +461,9 @@ apply_kernel(const __grid_constant__ KernelParams<CAP> prm) {
 
 // =============================================================================================
 // apply with clipping, v2: the same static two-pass schedule as apply_kernel, plus
-//   * an ON-CHIP STASH: the last `stash_tiles` tiles a CTA reduces in pass 1 never leave the SM --
-//     a' goes to shared memory instead of HBM/L2 and pass 2 (which walks the CTA's tiles in reverse)
-//     consumes it from there first.  3 CTAs x 9 tiles x 8 KB x 148 SMs = 32 MB of the 115 MB a'
+//   * an ON-CHIP STASH: the first `stash_tiles` tiles a CTA reduces in pass 1 never leave the SM --
+//     a' goes to shared memory instead of HBM/L2 and pass 2 (which walks the CTA's tiles in reverse,
+//     i.e. reaches them last, when L2 would long have evicted them) consumes it from there.  3 CTAs x 9 tiles x 8 KB x 148 SMs = 32 MB of the 115 MB a'
 //     slab at BERT-Small; what is left competes for far fewer L2 lines.
 //   * optionally an ordinary launch with an atomic grid barrier instead of a cooperative launch
 //     (kTuneOwnBarrier): the grid never exceeds the co-resident capacity, so the barrier cannot
@@ -469,6 +471,53 @@ apply_kernel(const __grid_constant__ KernelParams<CAP> prm) {
 // Thread t of a CTA reads back exactly the shared-memory words it wrote, so the stash needs no
 // synchronisation and is bank-conflict free (consecutive lanes, consecutive 16-byte words).
 // =============================================================================================
+// ---------------------------------------------------------------------------------------------
+// Tensor Memory as a scratchpad.  TMEM (256 KB per SM, 512 columns x 128 lanes x 32 bit) normally
+// holds tcgen05.mma accumulators; this kernel has no MMA, so it is idle silicon -- 37 MB across the
+// chip, more than the shared-memory stash.  A kernel that touches TMEM is limited to ONE CTA per
+// SM by the driver, so the TMEM variant runs 768-thread CTAs made of three 256-thread groups that
+// behave exactly like the three co-resident CTAs of the plain variant (virtual block id =
+// blockIdx * 3 + group).  The CTA allocates all 512 columns; every warp parks a' values in the 32
+// lanes it may address (lane quadrant = warp % 4; the 6 warps sharing a quadrant take 80 columns each):
+// tcgen05.st 32x32b.x8 writes the thread's 8 words of a tile to 8 consecutive columns of its own
+// lane, tcgen05.ld reads them back in pass 2.  A thread only ever reads what it wrote itself.
+// ---------------------------------------------------------------------------------------------
+constexpr int kGroups3 = 3;                       // 768-thread CTA = three 256-thread groups, one CTA per SM
+constexpr int kTmemCols = 512;                    // a TMEM-using kernel gets one CTA per SM: take all columns
+constexpr int kTmemColsPerWarp = 80;              // 6 warps share a lane quadrant: 6 x 80 = 480 <= 512
+constexpr int kTmemTiles = kTmemColsPerWarp / 8;  // 10 tiles per group
+constexpr uint32_t kNoTmem = 0xffffffffu;
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst) {
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "r"((uint32_t)kTmemCols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"((uint32_t)kTmemCols) : "memory");
+}
+__device__ __forceinline__ void tmem_store8(uint32_t taddr, const float4& a, const float4& b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)),
+                 "r"(__float_as_uint(a.w)), "r"(__float_as_uint(b.x)), "r"(__float_as_uint(b.y)),
+                 "r"(__float_as_uint(b.z)), "r"(__float_as_uint(b.w)) : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_load8(uint32_t taddr, float4& a, float4& b) {
+  uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  a = make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3));
+  b = make_float4(__uint_as_float(r4), __uint_as_float(r5), __uint_as_float(r6), __uint_as_float(r7));
+}
+// TMEM address of this warp's slot for stashed tile `slot` (0..kTmemTiles-1): lane quadrant = warp % 4,
+// column block = warp / 4 (0..5 across the three groups)
+__device__ __forceinline__ uint32_t tmem_slot_addr(uint32_t base, int slot) {
+  const uint32_t warp = threadIdx.x >> 5;
+  return base + (((warp & 3u) * 32u) << 16) + (warp >> 2) * kTmemColsPerWarp + (uint32_t)slot * 8u;
+}
+
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -484,13 +533,14 @@ __device__ __forceinline__ void atomic_grid_barrier(uint32_t* ctr, uint32_t targ
   __syncthreads();
 }
 
-template <bool HAS_G, int CAP>
+template <bool HAS_G, int CAP, bool USE_TMEM>
 __device__ __forceinline__ float norm_tile2(const TileDesc d, const KernelParams<CAP>& prm, float acc,
-                                            float4* __restrict__ stash, const uint64_t pol) {
+                                            float4* __restrict__ stash, const uint32_t tmem, const uint64_t pol) {
+  static_assert(kUnroll == 2, "the TMEM stash moves exactly two float4 per thread per tile");
   const float* __restrict__ g = nullptr;
   if constexpr (HAS_G) g = grad_ptr(prm.tab, d);
   float* __restrict__ a = prm.accum + (size_t)d.soff32 * kSlabAlign;
-  const uint32_t len = d.len, tid = threadIdx.x;
+  const uint32_t len = d.len, tid = threadIdx.x & (kThreads - 1);     // thread index inside the 256-thread group
   const float nf = prm.sc.nf;
   if (g == nullptr || aligned16(g)) {
     const uint32_t nvec = len >> 2;
@@ -500,7 +550,7 @@ __device__ __forceinline__ float norm_tile2(const TileDesc d, const KernelParams
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const uint32_t i = u * kThreads + tid;
-      if (i < nvec) { va[u] = stash ? __ldcs(a4 + i) : ld_policy(a4 + i, pol); if (g) vg[u] = ld_stream(g4 + i); }
+      if (i < nvec) { va[u] = (stash || tmem != kNoTmem) ? __ldcs(a4 + i) : ld_policy(a4 + i, pol); if (g) vg[u] = ld_stream(g4 + i); }
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
@@ -511,11 +561,15 @@ __device__ __forceinline__ float norm_tile2(const TileDesc d, const KernelParams
           va[u].z = __fadd_rn(va[u].z, vg[u].z); va[u].w = __fadd_rn(va[u].w, vg[u].w);
         }
         if (stash) stash[i] = va[u];
+        else if (tmem != kNoTmem) {}
         else if (g) st_policy(a4 + i, va[u], pol);
         const float nx = normalize(va[u].x, nf), ny = normalize(va[u].y, nf),
                     nz = normalize(va[u].z, nf), nw = normalize(va[u].w, nf);
         acc = fmaf(nx, nx, acc); acc = fmaf(ny, ny, acc); acc = fmaf(nz, nz, acc); acc = fmaf(nw, nw, acc);
       }
+    }
+    if constexpr (USE_TMEM) {
+      if (tmem != kNoTmem) tmem_store8(tmem, va[0], va[1]);   // full tile: every lane of every warp is here
     }
     const uint32_t i = (nvec << 2) + tid;      // < 4 tail elements always travel through global memory
     if (i < len) {
@@ -535,16 +589,16 @@ __device__ __forceinline__ float norm_tile2(const TileDesc d, const KernelParams
   return acc;
 }
 
-template <int VARIANT, int CAP>
+template <int VARIANT, int CAP, bool USE_TMEM>
 __device__ __forceinline__ void update_tile2(const TileDesc d, const KernelParams<CAP>& prm, const float s,
-                                             const float4* __restrict__ stash) {
+                                             const float4* __restrict__ stash, const uint32_t tmem) {
   const size_t soff = (size_t)d.soff32 * kSlabAlign;
   float* __restrict__ a = prm.accum + soff;
   float* __restrict__ m = prm.m + soff;
   float* __restrict__ v = prm.v + soff;
   float* __restrict__ p = param_ptr(prm.tab, d);
   const bool decay = (d.tensor_flags >> 31) != 0;
-  const uint32_t len = d.len, tid = threadIdx.x;
+  const uint32_t len = d.len, tid = threadIdx.x & (kThreads - 1);
   const Scalars& sc = prm.sc;
   auto elem = [&](float ax, float& px, float& mx, float& vx) {
     const float c = __fmul_rn(normalize(ax, sc.nf), s);     // optimization.py:83-84
@@ -562,8 +616,12 @@ __device__ __forceinline__ void update_tile2(const TileDesc d, const KernelParam
       const uint32_t i = u * kThreads + tid;
       if (i < nvec) {
         vp[u] = __ldcs(p4 + i); vm[u] = __ldcs(m4 + i); vv[u] = __ldcs(v4 + i);
-        va[u] = stash ? stash[i] : __ldcs(a4 + i);
+        if (stash) va[u] = stash[i];
+        else if (tmem == kNoTmem) va[u] = __ldcs(a4 + i);
       }
+    }
+    if constexpr (USE_TMEM) {
+      if (tmem != kNoTmem) tmem_load8(tmem, va[0], va[1]);
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
@@ -598,15 +656,38 @@ __device__ __forceinline__ bool stashable(const TileDesc& d, const KernelParams<
   return ok;
 }
 
-template <int VARIANT, bool HAS_G, int CAP>
-__global__ void __launch_bounds__(kThreads)
+template <int VARIANT, bool HAS_G, int CAP, bool USE_TMEM>
+__global__ void __launch_bounds__(kThreads * (USE_TMEM ? kGroups3 : 1))
 apply_clip2_kernel(const __grid_constant__ KernelParams<CAP> prm) {
-  extern __shared__ float4 stash_mem[];                 // stash_tiles x (kTile/4) float4
-  __shared__ double red[kThreads / 32];
+  constexpr int GROUPS = USE_TMEM ? kGroups3 : 1;
+  extern __shared__ float4 stash_all[];                 // GROUPS x stash_tiles x (kTile/4) float4
+  __shared__ double red[kThreads * GROUPS / 32];
   __shared__ float s_bcast[2];
-  const int nt = prm.num_tiles, G = (int)gridDim.x, b = (int)blockIdx.x;
+  const int grp = (int)threadIdx.x / kThreads;          // 256-thread group = virtual CTA
+  const int nt = prm.num_tiles, G = (int)gridDim.x * GROUPS, b = (int)blockIdx.x * GROUPS + grp;
+  float4* const stash_mem = stash_all + (size_t)grp * prm.stash_tiles * (kTile / 4);
   const int my_count = b < nt ? (nt - 1 - b) / G + 1 : 0;    // tiles b, b+G, ... of this CTA
-  const int first_stashed = my_count - min(my_count, prm.stash_tiles);
+  // Stash the OLDEST tiles of pass 1 (k < stash_tiles): pass 2 runs in reverse, so the youngest a'
+  // lines are still in L2 when they are needed, while the oldest would have been evicted long before
+  // pass 2 reaches them -- shared memory and L2 cover complementary ends of the sequence.
+  const int n_stashed = min(my_count, prm.stash_tiles);
+  // Tensor Memory takes the next-oldest tiles (full, vector-path tiles only: tcgen05.st/ld are
+  // warp-collective, every lane must carry data)
+  __shared__ uint32_t s_tmem_base;
+  const int n_tmem = USE_TMEM ? prm.tmem_tiles : 0;
+  if (USE_TMEM && n_tmem > 0) {
+    if (threadIdx.x < 32) tmem_alloc(&s_tmem_base);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  const uint32_t tmem_base = (USE_TMEM && n_tmem > 0) ? s_tmem_base : 0u;
+  auto tmem_for = [&](int k, const TileDesc& d) -> uint32_t {
+    if constexpr (!USE_TMEM) return kNoTmem;
+    const int slot = k - n_stashed;
+    if (slot < 0 || slot >= n_tmem || d.len != (uint32_t)kTile || !stashable<HAS_G>(d, prm)) return kNoTmem;
+    return tmem_slot_addr(tmem_base, slot);
+  };
   const uint64_t pol = policy_evict_last();
   const bool own_barrier = (prm.tune & kTuneOwnBarrier) != 0;
 
@@ -617,18 +698,18 @@ apply_clip2_kernel(const __grid_constant__ KernelParams<CAP> prm) {
     for (int k = 0; k < my_count; ++k) {
       TileDesc dn;
       if (k + 1 < my_count) dn = prm.tiles[b + (k + 1) * G];
-      float4* st = (k >= first_stashed && stashable<HAS_G>(d, prm)) ? stash_mem + (size_t)(k - first_stashed) * (kTile / 4) : nullptr;
-      acc += (double)norm_tile2<HAS_G>(d, prm, 0.f, st, pol);
+      float4* st = (k < n_stashed && stashable<HAS_G>(d, prm)) ? stash_mem + (size_t)k * (kTile / 4) : nullptr;
+      acc += (double)norm_tile2<HAS_G, CAP, USE_TMEM>(d, prm, 0.f, st, st ? kNoTmem : tmem_for(k, d), pol);
       d = dn;
     }
   }
   const double part = block_reduce_to_double(acc, red);
-  if (threadIdx.x == 0) prm.partials[b] = part;
-  if (own_barrier) atomic_grid_barrier(prm.tickets + 3, (uint32_t)G); else cg::this_grid().sync();
+  if (threadIdx.x == 0) prm.partials[blockIdx.x] = part;
+  if (own_barrier) atomic_grid_barrier(prm.tickets + 3, gridDim.x); else cg::this_grid().sync();
   // ---- every CTA combines the per-CTA partials in the same fixed order ---------------------------
   if (threadIdx.x < 32) {
     double tot = 0.0;
-    for (int i = threadIdx.x; i < G; i += 32) tot += __ldcg(prm.partials + i);
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) tot += __ldcg(prm.partials + i);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
     if (threadIdx.x == 0) {
@@ -645,19 +726,23 @@ apply_clip2_kernel(const __grid_constant__ KernelParams<CAP> prm) {
     for (int k = my_count - 1; k >= 0; --k) {
       TileDesc dn;
       if (k > 0) dn = prm.tiles[b + (k - 1) * G];
-      const float4* st = (k >= first_stashed && stashable<HAS_G>(d, prm)) ? stash_mem + (size_t)(k - first_stashed) * (kTile / 4) : nullptr;
-      update_tile2<VARIANT>(d, prm, s, st);
+      const float4* st = (k < n_stashed && stashable<HAS_G>(d, prm)) ? stash_mem + (size_t)k * (kTile / 4) : nullptr;
+      update_tile2<VARIANT, CAP, USE_TMEM>(d, prm, s, st, st ? kNoTmem : tmem_for(k, d));
       d = dn;
     }
   }
-  if (b == 0 && threadIdx.x == 0) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
     prm.stats[0] = 1.f; prm.stats[1] = prm.sc.lr; prm.stats[2] = gn; prm.stats[3] = s;
+  }
+  if (USE_TMEM && n_tmem > 0) {
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tmem_base);
   }
   if (own_barrier) {          // the last CTA to leave re-arms the barrier counter for the next launch
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();
-      if (atomicAdd(prm.tickets + 2, 1u) == (uint32_t)G - 1) { prm.tickets[3] = 0; prm.tickets[2] = 0; __threadfence(); }
+      if (atomicAdd(prm.tickets + 2, 1u) == gridDim.x - 1) { prm.tickets[3] = 0; prm.tickets[2] = 0; __threadfence(); }
     }
   }
 }
