@@ -250,14 +250,15 @@ def run_b200_arm(args):
     evs[0].record(stream)
     for i in range(K):
         kinds.append(micro_step(base + i))
-        evs[i + 1].record(stream)
+        if not args.no_launch_events or i == K - 1:
+            evs[i + 1].record(stream)
     torch.cuda.synchronize(dev)
     torch.cuda.profiler.stop()
     clocks = sampler.stop()
     if dist is not None:
         dist.barrier()
     total_ms = evs[0].elapsed_time(evs[K])
-    per = [evs[i].elapsed_time(evs[i + 1]) for i in range(K)]
+    per = [evs[i].elapsed_time(evs[i + 1]) for i in range(K)] if not args.no_launch_events else [total_ms / K] * K
     if dist is not None:
         t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -349,6 +350,7 @@ def main():
     ap.add_argument("--accum-n", type=int, default=0)
     ap.add_argument("--sigma", type=float, default=1e-3, help="gradient std; 1e-3 clips at BERT-Small, 1e-4 does not")
     ap.add_argument("--dp", default="fused", choices=["fused", "allreduce"], help="multi-GPU exchange: in-kernel over peer memory, or NCCL all-reduce baseline")
+    ap.add_argument("--no-launch-events", action="store_true", help="experiment: time only the whole region (no event between launches)")
     ap.add_argument("--no-clip", action="store_true", help="experiment: AdamWeightDecay without clip_by_global_norm (single-pass apply)")
     ap.add_argument("--e2e-steps", type=int, default=48)
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-oracle timing (0 disables)")

@@ -63,6 +63,7 @@ struct gaccum_plan {
   uint32_t* d_tickets = nullptr;
   float* d_stats = nullptr;
   float* d_bcast = nullptr;
+  unsigned long long* d_debug = nullptr;   // GACCUM_EXPERIMENTS only
   int num_sms = 0;
   int max_grid = 0;
   uint32_t tune = 0;   // kTune* bits; GACCUM_TUNE overrides (experiments)
@@ -106,6 +107,10 @@ static int build_layout(gaccum_plan* pl) {
 static Scalars make_scalars(const gaccum_hparams& hp, const gaccum_step_args* a) {
   Scalars s{};
   s.nf = a ? (float)a->accum_n : 1.0f;
+  {
+    const int32_t n = a ? a->accum_n : 1;
+    s.inv_nf = (n > 0 && (n & (n - 1)) == 0 && n <= (1 << 24)) ? 1.0f / (float)n : 0.0f;
+  }
   s.lr = a ? a->lr : 0.0f;
   s.b1 = (float)hp.beta1;
   s.b2 = (float)hp.beta2;
@@ -274,6 +279,7 @@ static void fill_common(gaccum_plan* pl, KernelParams<CAP>& prm, float* accum, f
   prm.partials = pl->d_partials;
   prm.tile_sumsq = pl->d_tile_sumsq;
   prm.tickets = pl->d_tickets;
+  prm.debug = pl->d_debug;
   prm.stats = pl->d_stats;
   prm.tune = pl->tune;
   prm.sc = sc;
@@ -453,11 +459,15 @@ int gaccum_plan_create(gaccum_plan** out, int32_t T, const int64_t* numels, cons
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_tickets, sizeof(uint32_t) * 4);
     if (e == cudaSuccess) e = cudaMemset(pl->d_tickets, 0, sizeof(uint32_t) * 4);
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_bcast, 4 * sizeof(float));
+    if (e == cudaSuccess && getenv("GACCUM_EXPERIMENTS")) {
+      e = cudaMalloc(&pl->d_debug, sizeof(unsigned long long) * 4 * (size_t)pl->max_grid);
+      if (e == cudaSuccess) e = cudaMemset(pl->d_debug, 0, sizeof(unsigned long long) * 4 * (size_t)pl->max_grid);
+    }
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_stats, sizeof(gaccum_stats));
     if (e == cudaSuccess) e = cudaMemset(pl->d_stats, 0, sizeof(gaccum_stats));
     if (e != cudaSuccess) {
       cudaFree(pl->d_tiles); cudaFree(pl->d_partials); cudaFree(pl->d_stats);
-    cudaFree(pl->d_tile_sumsq); cudaFree(pl->d_tickets); cudaFree(pl->d_bcast);
+    cudaFree(pl->d_tile_sumsq); cudaFree(pl->d_tickets); cudaFree(pl->d_bcast); cudaFree(pl->d_debug);
       delete pl;
       return fail(GACCUM_ECUDA, "plan device setup failed: %s", cudaGetErrorString(e));
     }
@@ -472,7 +482,7 @@ int gaccum_plan_destroy(gaccum_plan* pl) {
   if (pl->device >= 0) {
     DeviceGuard guard(pl->device);
     cudaFree(pl->d_tiles); cudaFree(pl->d_partials); cudaFree(pl->d_stats);
-    cudaFree(pl->d_tile_sumsq); cudaFree(pl->d_tickets); cudaFree(pl->d_bcast);
+    cudaFree(pl->d_tile_sumsq); cudaFree(pl->d_tickets); cudaFree(pl->d_bcast); cudaFree(pl->d_debug);
   }
   delete pl;
   return GACCUM_OK;
@@ -759,6 +769,14 @@ int gaccum_host_session_sync(gaccum_host_session* s) {
 int gaccum_host_session_slabs(gaccum_host_session* s, float** out) {
   if (!s || !out) return fail(GACCUM_EINVAL, "bad arguments to gaccum_host_session_slabs");
   out[0] = s->d_params; out[1] = s->d_accum; out[2] = s->d_m; out[3] = s->d_v;
+  return GACCUM_OK;
+}
+
+// Experiments only (not declared in gaccum.h): per-CTA timestamps of the last clip-apply launch.
+extern "C" __attribute__((visibility("default"))) int gaccum_debug_read(gaccum_plan* pl, unsigned long long* out, int n) {
+  if (!pl || !pl->d_debug) return fail(GACCUM_EINVAL, "no debug buffer (set GACCUM_EXPERIMENTS=1 before creating the plan)");
+  DeviceGuard guard(pl->device);
+  CUDA_TRY(cudaMemcpy(out, pl->d_debug, sizeof(unsigned long long) * (size_t)std::min(n, 4 * pl->max_grid), cudaMemcpyDeviceToHost));
   return GACCUM_OK;
 }
 

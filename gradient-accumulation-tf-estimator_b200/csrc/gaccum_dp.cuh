@@ -91,7 +91,7 @@ template <int TPI>
 __device__ __forceinline__ float dp_reduce_tiles(const TileDesc (&d)[TPI], const int ntile, const DpParams& prm,
                                                  float acc, const uint64_t pol) {
   const uint32_t tid = threadIdx.x;
-  const float nf = prm.sc.nf;
+  const float nf = prm.sc.nf, inv_nf = prm.sc.inv_nf;
   const int W = prm.world;
   float4 part[TPI][kUnroll][kMaxRanks / (TPI > 1 ? (TPI > 2 ? 4 : 2) : 1)];
   constexpr int WCAP = kMaxRanks / (TPI > 1 ? (TPI > 2 ? 4 : 2) : 1);   // TPI=4 -> W<=2, TPI=2 -> W<=4, TPI=1 -> W<=8
@@ -129,7 +129,7 @@ __device__ __forceinline__ float dp_reduce_tiles(const TileDesc (&d)[TPI], const
               s.z = __fadd_rn(s.z, part[j][u][w].z); s.w = __fadd_rn(s.w, part[j][u][w].w);
             }
           st_policy(mine + i, s, pol);
-          const float nx = normalize(s.x, nf), ny = normalize(s.y, nf), nz = normalize(s.z, nf), nw = normalize(s.w, nf);
+          const float nx = normalize(s.x, nf, inv_nf), ny = normalize(s.y, nf, inv_nf), nz = normalize(s.z, nf, inv_nf), nw = normalize(s.w, nf, inv_nf);
           acc = fmaf(nx, nx, acc); acc = fmaf(ny, ny, acc); acc = fmaf(nz, nz, acc); acc = fmaf(nw, nw, acc);
         }
       }
@@ -138,7 +138,7 @@ __device__ __forceinline__ float dp_reduce_tiles(const TileDesc (&d)[TPI], const
         float s = ld_peer(prm.accum[0] + soff + i);
         for (int w = 1; w < W; ++w) s = __fadd_rn(s, ld_peer(prm.accum[w] + soff + i));
         prm.accum[prm.rank][soff + i] = s;
-        const float n = normalize(s, nf);
+        const float n = normalize(s, nf, inv_nf);
         acc = fmaf(n, n, acc);
       }
     }
@@ -174,7 +174,7 @@ __device__ __forceinline__ void dp_update_tile(const TileDesc d, const DpParams&
   const Scalars& sc = prm.sc;
   const int W = prm.world;
   auto elem = [&](float ax, float& px, float& mx, float& vx) {
-    const float c = sc.clip > 0.f ? __fmul_rn(normalize(ax, sc.nf), s) : normalize(ax, sc.nf);
+    const float c = sc.clip > 0.f ? __fmul_rn(normalize(ax, sc.nf, sc.inv_nf), s) : normalize(ax, sc.nf, sc.inv_nf);
     adam_elem<VARIANT>(c, px, mx, vx, decay, sc);
   };
   float4* a4 = reinterpret_cast<float4*>(a);

@@ -57,6 +57,7 @@ struct PtrTable<0> {
 
 struct Scalars {
   float nf;      // fp32(N)                                   optimization.py:83
+  float inv_nf;  // 1/N when N is a power of two (exact), else 0 -> the kernels divide
   float lr;      // learning rate of this micro-step          optimization.py:29-54
   float b1, b2;  // fp32(beta)                                optimization.py:151,153
   float omb1;    // A: fp32(1.0 - beta1) from double (:152);  B: 1.0f - fp32(beta1)
@@ -81,6 +82,7 @@ struct KernelParams {
   uint32_t tune;      // kTune* bits (cache-policy experiments; uniform branches)
   int32_t stash_tiles;  // apply_clip2_kernel: tiles of a' each CTA keeps in shared memory between the passes
   int32_t tmem_tiles;   // ... and in Tensor Memory (0 or kTmemTiles)
+  unsigned long long* debug;  // GACCUM_EXPERIMENTS: 4 timestamps (ns) per CTA, else nullptr
   Scalars sc;
   PtrTable<CAP> tab;
 };
@@ -101,7 +103,16 @@ constexpr uint32_t kTuneSkipZero = 64u;    // TIMING EXPERIMENTS ONLY (dp kernel
 // accumulator is a streaming store.  a' must survive in L2 from pass 1 to pass 2, so it can be
 // tagged evict_last while everything that is touched once is tagged evict-first.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+#ifdef GACCUM_G_NC
+  float4 v;   // G is never written by these kernels: read-only path, no L1 allocation
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+#else
+  return __ldcs(p);
+#endif
+}
 __device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
 __device__ __forceinline__ uint64_t policy_evict_last() {
   uint64_t pol;
@@ -141,8 +152,12 @@ __device__ __forceinline__ bool aligned16(const void* p) { return ((uintptr_t)p 
 // ---------------------------------------------------------------------------------------------
 // per-element math, one rounding per reference op
 // ---------------------------------------------------------------------------------------------
-// optimization.py:83  (1.0*a)/N  -- the multiply by 1.0 is exact
-__device__ __forceinline__ float normalize(float a, float nf) { return __fdiv_rn(a, nf); }
+// optimization.py:83  (1.0*a)/N  -- the multiply by 1.0 is exact.  When N is a power of two, 1/N is
+// exact and a * (1/N) is the same correctly rounded real number as a / N (bit-identical, subnormals
+// included), which saves a ~12-instruction IEEE division per element; otherwise divide.
+__device__ __forceinline__ float normalize(float a, float nf, float inv_nf) {
+  return inv_nf != 0.f ? __fmul_rn(a, inv_nf) : __fdiv_rn(a, nf);
+}
 
 template <int VARIANT>
 __device__ __forceinline__ void adam_elem(float c, float& p, float& m, float& v, bool decay,
@@ -238,7 +253,7 @@ __device__ __forceinline__ float norm_tile(const TileDesc d, const KernelParams<
   if constexpr (HAS_G) g = grad_ptr(prm.tab, d);
   float* __restrict__ a = prm.accum + (size_t)d.soff32 * kSlabAlign;
   const uint32_t len = d.len, tid = threadIdx.x;
-  const float nf = prm.sc.nf;
+  const float nf = prm.sc.nf, inv_nf = prm.sc.inv_nf;
   const bool keep = (prm.tune & kTuneKeepA) != 0;
   const uint64_t pol = policy_evict_last();
   if (g == nullptr || aligned16(g)) {
@@ -260,8 +275,8 @@ __device__ __forceinline__ float norm_tile(const TileDesc d, const KernelParams<
           va[u].z = __fadd_rn(va[u].z, vg[u].z); va[u].w = __fadd_rn(va[u].w, vg[u].w);
           if (keep) st_policy(a4 + i, va[u], pol); else a4[i] = va[u];
         }
-        const float nx = normalize(va[u].x, nf), ny = normalize(va[u].y, nf),
-                    nz = normalize(va[u].z, nf), nw = normalize(va[u].w, nf);
+        const float nx = normalize(va[u].x, nf, inv_nf), ny = normalize(va[u].y, nf, inv_nf),
+                    nz = normalize(va[u].z, nf, inv_nf), nw = normalize(va[u].w, nf, inv_nf);
         acc = fmaf(nx, nx, acc); acc = fmaf(ny, ny, acc); acc = fmaf(nz, nz, acc); acc = fmaf(nw, nw, acc);
       }
     }
@@ -269,14 +284,14 @@ __device__ __forceinline__ float norm_tile(const TileDesc d, const KernelParams<
     if (i < len) {
       float x = a[i];
       if (g) { x = __fadd_rn(x, ld_stream(g + i)); a[i] = x; }
-      const float n = normalize(x, nf);
+      const float n = normalize(x, nf, inv_nf);
       acc = fmaf(n, n, acc);
     }
   } else {
     for (uint32_t i = tid; i < len; i += kThreads) {
       const float x = __fadd_rn(a[i], ld_stream(g + i));
       a[i] = x;
-      const float n = normalize(x, nf);
+      const float n = normalize(x, nf, inv_nf);
       acc = fmaf(n, n, acc);
     }
   }
@@ -301,7 +316,7 @@ __device__ __forceinline__ void update_tile(const TileDesc d, const KernelParams
 
   auto elem = [&](float ax, float gx, float& px, float& mx, float& vx) {
     if (LOAD_G) ax = __fadd_rn(ax, gx);               // optimization.py:81 (gx = 0 never used: see callers)
-    float c = normalize(ax, sc.nf);                    // :83
+    float c = normalize(ax, sc.nf, sc.inv_nf);                    // :83
     if (CLIP) c = __fmul_rn(c, s);                     // :84
     adam_elem<VARIANT>(c, px, mx, vx, decay, sc);      // :85
   };
@@ -334,7 +349,7 @@ __device__ __forceinline__ void update_tile(const TileDesc d, const KernelParams
         } else {
           // no gradient for this tile: a + 0 would turn -0 into +0 only; skip the add entirely
           auto e0 = [&](float ax, float& px, float& mx, float& vx) {
-            float c = normalize(ax, sc.nf);
+            float c = normalize(ax, sc.nf, sc.inv_nf);
             if (CLIP) c = __fmul_rn(c, s);
             adam_elem<VARIANT>(c, px, mx, vx, decay, sc);
           };
@@ -350,7 +365,7 @@ __device__ __forceinline__ void update_tile(const TileDesc d, const KernelParams
     if (i < len) {
       float ax = a[i], px = p[i], mx = m[i], vx = v[i];
       if (LOAD_G && g) ax = __fadd_rn(ax, ld_stream(g + i));
-      float c = normalize(ax, sc.nf);
+      float c = normalize(ax, sc.nf, sc.inv_nf);
       if (CLIP) c = __fmul_rn(c, s);
       adam_elem<VARIANT>(c, px, mx, vx, decay, sc);
       p[i] = px; m[i] = mx; v[i] = vx; a[i] = 0.f;
@@ -359,7 +374,7 @@ __device__ __forceinline__ void update_tile(const TileDesc d, const KernelParams
     for (uint32_t i = tid; i < len; i += kThreads) {
       float ax = a[i], px = p[i], mx = m[i], vx = v[i];
       if (LOAD_G && g) ax = __fadd_rn(ax, ld_stream(g + i));
-      float c = normalize(ax, sc.nf);
+      float c = normalize(ax, sc.nf, sc.inv_nf);
       if (CLIP) c = __fmul_rn(c, s);
       adam_elem<VARIANT>(c, px, mx, vx, decay, sc);
       p[i] = px; m[i] = mx; v[i] = vx; a[i] = 0.f;
@@ -533,56 +548,77 @@ __device__ __forceinline__ void atomic_grid_barrier(uint32_t* ctr, uint32_t targ
   __syncthreads();
 }
 
-template <bool HAS_G, int CAP, bool USE_TMEM>
-__device__ __forceinline__ float norm_tile2(const TileDesc d, const KernelParams<CAP>& prm, float acc,
-                                            float4* __restrict__ stash, const uint32_t tmem, const uint64_t pol) {
-  static_assert(kUnroll == 2, "the TMEM stash moves exactly two float4 per thread per tile");
-  const float* __restrict__ g = nullptr;
-  if constexpr (HAS_G) g = grad_ptr(prm.tab, d);
-  float* __restrict__ a = prm.accum + (size_t)d.soff32 * kSlabAlign;
-  const uint32_t len = d.len, tid = threadIdx.x & (kThreads - 1);     // thread index inside the 256-thread group
-  const float nf = prm.sc.nf;
-  if (g == nullptr || aligned16(g)) {
-    const uint32_t nvec = len >> 2;
-    const float4* g4 = reinterpret_cast<const float4*>(g);
-    float4* a4 = reinterpret_cast<float4*>(a);
-    float4 vg[kUnroll], va[kUnroll];
+// Pass 1 is split into "issue the loads" and "finish", so that the loads of several tiles can be in
+// flight before the first one is consumed: with one tile at a time a thread has only 4 LDG.128
+// outstanding (49 KB per SM), and the measured per-CTA timeline shows pass 1 latency-bound at
+// 4.4 TB/s; with kPass1Tiles tiles the SM keeps >= 100 KB in flight and the pass becomes HBM-bound.
+constexpr int kPass1Tiles = 2;
+struct NormRegs {
+  float4 va[kUnroll], vg[kUnroll];
+  const float* g;
+  bool vec;          // false: unaligned gradient pointer -> scalar path, nothing was loaded
+};
+
+template <bool HAS_G, int CAP>
+__device__ __forceinline__ void norm_issue(const TileDesc& d, const KernelParams<CAP>& prm, const bool on_chip,
+                                           const uint64_t pol, NormRegs& r) {
+  r.g = nullptr;
+  if constexpr (HAS_G) r.g = grad_ptr(prm.tab, d);
+  r.vec = (r.g == nullptr || aligned16(r.g));
+  if (!r.vec) return;
+  const float4* g4 = reinterpret_cast<const float4*>(r.g);
+  const float4* a4 = reinterpret_cast<const float4*>(prm.accum + (size_t)d.soff32 * kSlabAlign);
+  const uint32_t nvec = d.len >> 2, tid = threadIdx.x & (kThreads - 1);   // thread index inside the 256-thread group
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const uint32_t i = u * kThreads + tid;
-      if (i < nvec) { va[u] = (stash || tmem != kNoTmem) ? __ldcs(a4 + i) : ld_policy(a4 + i, pol); if (g) vg[u] = ld_stream(g4 + i); }
-    }
+  for (int u = 0; u < kUnroll; ++u) {
+    const uint32_t i = u * kThreads + tid;
+    if (i < nvec) { r.va[u] = on_chip ? __ldcs(a4 + i) : ld_policy(a4 + i, pol); if (r.g) r.vg[u] = ld_stream(g4 + i); }
+  }
+}
+
+template <bool HAS_G, int CAP, bool USE_TMEM>
+__device__ __forceinline__ float norm_finish(const TileDesc& d, const KernelParams<CAP>& prm, NormRegs& r,
+                                             float4* __restrict__ stash, const uint32_t tmem, const uint64_t pol) {
+  static_assert(kUnroll == 2, "the TMEM stash moves exactly two float4 per thread per tile");
+  const float* __restrict__ g = r.g;
+  float* __restrict__ a = prm.accum + (size_t)d.soff32 * kSlabAlign;
+  const uint32_t len = d.len, tid = threadIdx.x & (kThreads - 1);
+  const float nf = prm.sc.nf, inv_nf = prm.sc.inv_nf;
+  float acc = 0.f;
+  if (r.vec) {
+    const uint32_t nvec = len >> 2;
+    float4* a4 = reinterpret_cast<float4*>(a);
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const uint32_t i = u * kThreads + tid;
       if (i < nvec) {
+        float4& x = r.va[u];
         if (g) {
-          va[u].x = __fadd_rn(va[u].x, vg[u].x); va[u].y = __fadd_rn(va[u].y, vg[u].y);
-          va[u].z = __fadd_rn(va[u].z, vg[u].z); va[u].w = __fadd_rn(va[u].w, vg[u].w);
+          x.x = __fadd_rn(x.x, r.vg[u].x); x.y = __fadd_rn(x.y, r.vg[u].y);
+          x.z = __fadd_rn(x.z, r.vg[u].z); x.w = __fadd_rn(x.w, r.vg[u].w);
         }
-        if (stash) stash[i] = va[u];
+        if (stash) stash[i] = x;
         else if (tmem != kNoTmem) {}
-        else if (g) st_policy(a4 + i, va[u], pol);
-        const float nx = normalize(va[u].x, nf), ny = normalize(va[u].y, nf),
-                    nz = normalize(va[u].z, nf), nw = normalize(va[u].w, nf);
+        else if (g) st_policy(a4 + i, x, pol);
+        const float nx = normalize(x.x, nf, inv_nf), ny = normalize(x.y, nf, inv_nf), nz = normalize(x.z, nf, inv_nf), nw = normalize(x.w, nf, inv_nf);
         acc = fmaf(nx, nx, acc); acc = fmaf(ny, ny, acc); acc = fmaf(nz, nz, acc); acc = fmaf(nw, nw, acc);
       }
     }
     if constexpr (USE_TMEM) {
-      if (tmem != kNoTmem) tmem_store8(tmem, va[0], va[1]);   // full tile: every lane of every warp is here
+      if (tmem != kNoTmem) tmem_store8(tmem, r.va[0], r.va[1]);   // full tile: every lane of every warp is here
     }
     const uint32_t i = (nvec << 2) + tid;      // < 4 tail elements always travel through global memory
     if (i < len) {
       float x = a[i];
       if (g) { x = __fadd_rn(x, ld_stream(g + i)); a[i] = x; }
-      const float n = normalize(x, nf);
+      const float n = normalize(x, nf, inv_nf);
       acc = fmaf(n, n, acc);
     }
   } else {
     for (uint32_t i = tid; i < len; i += kThreads) {
       const float x = __fadd_rn(a[i], ld_stream(g + i));
       a[i] = x;
-      const float n = normalize(x, nf);
+      const float n = normalize(x, nf, inv_nf);
       acc = fmaf(n, n, acc);
     }
   }
@@ -601,7 +637,7 @@ __device__ __forceinline__ void update_tile2(const TileDesc d, const KernelParam
   const uint32_t len = d.len, tid = threadIdx.x & (kThreads - 1);
   const Scalars& sc = prm.sc;
   auto elem = [&](float ax, float& px, float& mx, float& vx) {
-    const float c = __fmul_rn(normalize(ax, sc.nf), s);     // optimization.py:83-84
+    const float c = __fmul_rn(normalize(ax, sc.nf, sc.inv_nf), s);     // optimization.py:83-84
     adam_elem<VARIANT>(c, px, mx, vx, decay, sc);           // :85
   };
   if (aligned16(p)) {
@@ -691,21 +727,41 @@ apply_clip2_kernel(const __grid_constant__ KernelParams<CAP> prm) {
   const uint64_t pol = policy_evict_last();
   const bool own_barrier = (prm.tune & kTuneOwnBarrier) != 0;
 
-  // ---- pass 1 ------------------------------------------------------------------------------------
-  double acc = 0.0;
-  if (my_count > 0) {
-    TileDesc d = prm.tiles[b];
-    for (int k = 0; k < my_count; ++k) {
-      TileDesc dn;
-      if (k + 1 < my_count) dn = prm.tiles[b + (k + 1) * G];
-      float4* st = (k < n_stashed && stashable<HAS_G>(d, prm)) ? stash_mem + (size_t)k * (kTile / 4) : nullptr;
-      acc += (double)norm_tile2<HAS_G, CAP, USE_TMEM>(d, prm, 0.f, st, st ? kNoTmem : tmem_for(k, d), pol);
-      d = dn;
+  auto stamp = [&](int which) {
+    if (prm.debug && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      prm.debug[blockIdx.x * 4 + which] = t;
     }
+  };
+  stamp(0);
+  // ---- pass 1: kPass1Tiles tiles per iteration, all loads issued before the first is consumed ----
+  double acc = 0.0;
+  for (int k0 = 0; k0 < my_count; k0 += kPass1Tiles) {
+    TileDesc d[kPass1Tiles];
+    NormRegs r[kPass1Tiles];
+    float4* st[kPass1Tiles];
+    uint32_t tm[kPass1Tiles];
+#pragma unroll
+    for (int j = 0; j < kPass1Tiles; ++j) {
+      const int k = k0 + j;
+      if (k < my_count) {
+        d[j] = prm.tiles[b + k * G];
+        st[j] = (k < n_stashed && stashable<HAS_G>(d[j], prm)) ? stash_mem + (size_t)k * (kTile / 4) : nullptr;
+        tm[j] = st[j] ? kNoTmem : tmem_for(k, d[j]);
+        norm_issue<HAS_G>(d[j], prm, st[j] != nullptr || tm[j] != kNoTmem, pol, r[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kPass1Tiles; ++j)
+      if (k0 + j < my_count)      // tile partials are added in tile order: the sum does not depend on kPass1Tiles
+        acc += (double)norm_finish<HAS_G, CAP, USE_TMEM>(d[j], prm, r[j], st[j], tm[j], pol);
   }
   const double part = block_reduce_to_double(acc, red);
   if (threadIdx.x == 0) prm.partials[blockIdx.x] = part;
+  stamp(1);
   if (own_barrier) atomic_grid_barrier(prm.tickets + 3, gridDim.x); else cg::this_grid().sync();
+  stamp(2);
   // ---- every CTA combines the per-CTA partials in the same fixed order ---------------------------
   if (threadIdx.x < 32) {
     double tot = 0.0;
@@ -731,6 +787,8 @@ apply_clip2_kernel(const __grid_constant__ KernelParams<CAP> prm) {
       d = dn;
     }
   }
+  __syncthreads();
+  stamp(3);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     prm.stats[0] = 1.f; prm.stats[1] = prm.sc.lr; prm.stats[2] = gn; prm.stats[3] = s;
   }

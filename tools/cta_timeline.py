@@ -1,0 +1,35 @@
+#!/usr/bin/env python
+"""Per-CTA timeline of the clip-apply kernel (GACCUM_EXPERIMENTS=1): where does each CTA wait?"""
+import ctypes as C, os, sys
+os.environ["GACCUM_EXPERIMENTS"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.join(sys.path[0], "oracle"))
+import numpy as np, torch
+import gaccum_b200 as g, oracle_np as onp
+from gaccum_b200.train_op import GaccumTrainOp
+from gaccum_b200 import _lib
+man = onp.MANIFESTS["bert_small"]()
+dev = torch.device("cuda:0")
+sets = []
+for r in range(3):
+    params = [torch.randn(s, device=dev) * 0.02 for _, s in man]
+    op = GaccumTrainOp(params, [n for n, _ in man], g.HParams.bert(), 4, lambda s: 1e-5, global_step=100001)
+    grads = [torch.randn(s, device=dev) * 1e-3 for _, s in man]
+    sets.append((op, op.bind(grads)))
+L = _lib._load()
+L.gaccum_debug_read.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+for it in range(12):
+    for op, b in sets:
+        op.run_bound(b)
+torch.cuda.synchronize()
+op = sets[0][0]
+buf = (C.c_ulonglong * (4 * 148))()
+assert L.gaccum_debug_read(op.plan._h, buf, 4 * 148) == 0
+t = np.array(buf, dtype=np.float64).reshape(148, 4)
+t0 = t[:, 0].min()
+t = (t - t0) / 1e3
+for name, col in (("start", 0), ("pass1 done", 1), ("barrier out", 2), ("pass2 done", 3)):
+    c = t[:, col]
+    print(f"{name:12s} min {c.min():7.1f}  median {np.median(c):7.1f}  max {c.max():7.1f} us   spread {c.max()-c.min():6.1f}")
+p1 = t[:, 1] - t[:, 0]; p2 = t[:, 3] - t[:, 2]
+print(f"pass1 duration per CTA: min {p1.min():.1f} median {np.median(p1):.1f} max {p1.max():.1f}; waiting at barrier: mean {np.mean(t[:,2]-t[:,1]):.1f} us")
+print(f"pass2 duration per CTA: min {p2.min():.1f} median {np.median(p2):.1f} max {p2.max():.1f}; idle before kernel end: mean {np.mean(t[:,3].max()-t[:,3]):.1f} us")
