@@ -300,6 +300,12 @@ def run_b200_arm(args):
                        "replicas are independent at N>1 (no exchange on this path)"}
         del hop
 
+    # ---- with the model in the loop: PyTorch BERT forward/backward (NOT our path) produces the
+    #      gradients, then the same train_op; shows what the exchange costs in a real micro-step ----
+    with_model = None
+    if args.model_steps > 0 and wl in ("bert_small", "bert_base", "bert_large"):
+        with_model = with_model_leg(args, wl, N, hp, lr_fn, world, rank, dev, dist)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -332,12 +338,73 @@ def run_b200_arm(args):
     }
     if e2e:
         out["e2e"] = e2e
+    if with_model:
+        out["with_model"] = with_model
     if world == 1 and args.cpu_budget > 0:
         _, info, _ = cpu_reference(wl, N, args.cpu_budget, variant_b)
         out["cpu_baseline"] = info
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def with_model_leg(args, wl, N, hp, lr_fn, world, rank, dev, dist):
+    import torch
+    from gaccum_b200.train_op import GaccumTrainOp
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bert_producer as bp
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    shape = {"bert_small": (8, 128), "bert_base": (32, 128), "bert_large": (4, 512)}[wl]
+    torch.manual_seed(7)
+    model = bp.Bert(wl).to(dev)
+    named = bp.tf_names(model)
+    params, names = [p for _, p in named], [n for n, _ in named]
+    if world > 1 and args.dp == "fused":
+        from gaccum_b200.distributed import FusedDataParallelTrainOp
+        runner = FusedDataParallelTrainOp(params, names, hp, N, lr_fn, global_step=1)
+    elif world > 1:
+        from gaccum_b200.distributed import DataParallelTrainOp
+        runner = DataParallelTrainOp(GaccumTrainOp(params, names, hp, N, lr_fn, global_step=1), None)
+    else:
+        runner = GaccumTrainOp(params, names, hp, N, lr_fn, global_step=1)
+    gen = torch.Generator(device=dev); gen.manual_seed(100 + rank)
+    batches = [bp.synthetic_batch(shape[0], shape[1], dev, gen) for _ in range(8)]
+    stream = torch.cuda.current_stream(dev)
+    t_op = [0.0]
+
+    def step(i, timed=False):
+        loss = model(*batches[i % 8]) / world                      # 04:46 loss / num_workers
+        grads = torch.autograd.grad(loss, params)
+        if timed:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); runner.run(grads); b.record(stream)
+            return a, b
+        runner.run(grads)
+
+    for i in range(2 * N):
+        step(i)
+    torch.cuda.synchronize(dev)
+    if dist is not None:
+        dist.barrier()
+    Km = args.model_steps
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pairs = []
+    e0.record(stream)
+    for i in range(Km):
+        pairs.append(step(i, timed=True))
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    op_ms = sum(a.elapsed_time(b) for a, b in pairs)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"value": world * Km / (ms * 1e-3), "unit": "micro-steps/s", "steps": Km, "ms_per_step": ms / Km,
+            "train_op_ms_per_step": op_ms / Km, "train_op_share": op_ms / ms,
+            "producer": f"tools/bert_producer.py {wl} micro_bs={shape[0]} seq_len={shape[1]} fp32 params, TF32 matmuls, torch SDPA",
+            "note": "forward/backward is plain PyTorch and is not part of this repository's path; it only supplies gradients"}
 
 
 def main():
@@ -352,6 +419,7 @@ def main():
     ap.add_argument("--dp", default="fused", choices=["fused", "allreduce"], help="multi-GPU exchange: in-kernel over peer memory, or NCCL all-reduce baseline")
     ap.add_argument("--no-launch-events", action="store_true", help="experiment: time only the whole region (no event between launches)")
     ap.add_argument("--no-clip", action="store_true", help="experiment: AdamWeightDecay without clip_by_global_norm (single-pass apply)")
+    ap.add_argument("--model-steps", type=int, default=48, help="micro-steps of the with-model leg (0 disables)")
     ap.add_argument("--e2e-steps", type=int, default=48)
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-oracle timing (0 disables)")
     args = ap.parse_args()
