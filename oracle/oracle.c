@@ -18,6 +18,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define ORACLE_API __attribute__((visibility("default")))
 
@@ -203,13 +206,21 @@ ORACLE_API int oracle_step(int32_t T, const int64_t* numel, float* const* params
   return 0;
 }
 
+ORACLE_API void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 ORACLE_API int oracle_num_threads(void) {
   int n = 1;
 #ifdef _OPENMP
 #pragma omp parallel
   {
 #pragma omp master
-    n = __builtin_omp_get_num_threads();
+    n = omp_get_num_threads();
   }
 #endif
   return n;

@@ -50,6 +50,7 @@ def lib():
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_HP), C.c_int64,
                                      C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.oracle_num_threads.restype = C.c_int
+        _lib.oracle_set_num_threads.argtypes = [C.c_int]
     return _lib
 
 
@@ -60,6 +61,10 @@ def learning_rate(init_lr, num_train_steps, num_warmup_steps, global_step) -> np
 
 def num_threads() -> int:
     return int(lib().oracle_num_threads())
+
+
+def set_num_threads(n: int) -> None:
+    lib().oracle_set_num_threads(int(n))
 
 
 def _ptr_array(arrs: Sequence[Optional[np.ndarray]]):
