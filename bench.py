@@ -354,7 +354,8 @@ def run_b200_arm(args):
                                                    if args.dp == "fused" else " nccl all-reduce of the packed accum slab on apply steps"),
                    "l2": f"rotating {R} independent state sets ({R * 5 * 4 * P / 1e6:.0f} MB of state+grads per rotation) > 126 MB L2",
                    "apply_launches": len(apply_ms), "accumulate_launches": len(acc_ms)},
-        "roofline": {"bound": "hbm", "kernel": "apply_clip2_kernel (a+=G, /N, global-norm clip, AdamWeightDecay, a=0; one cooperative launch)",
+        "roofline": {"bound": "hbm", "kernel": ("apply_clip2_kernel (a+=G, /N, global-norm clip, AdamWeightDecay, a=0; one cooperative launch)" if world == 1 else
+                                          "accumulate_kernel + dp_apply_kernel (apply step at N>1: includes the NVLink exchange, so this is not an HBM roofline)"),
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "algorithmic_bytes": ab, "avg_launch_us": a_ms * 1e3,
                      "traffic": measured_traffic(wl) if (world == 1 and not args.no_clip) else None,
@@ -362,7 +363,8 @@ def run_b200_arm(args):
         "roofline_accumulate": {"bound": "hbm", "kernel": "accumulate_kernel", "achieved": acb / (c_ms * 1e-3) / 1e9 if acc_ms else None,
                                 "peak": peak, "unit": "GB/s", "frac": (acb / (c_ms * 1e-3) / 1e9 / peak) if acc_ms else None,
                                 "algorithmic_bytes": acb, "avg_launch_us": c_ms * 1e3 if acc_ms else None},
-        "gpu_launches": K, "clocks": clocks,
+        "gpu_launches": K + (len(apply_ms) if world > 1 else 0),   # DP apply steps = local accumulate + fused exchange/apply kernel
+        "clocks": clocks,
     }
     if e2e:
         out["e2e"] = e2e
