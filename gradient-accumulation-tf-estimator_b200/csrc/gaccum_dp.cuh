@@ -79,7 +79,7 @@ __device__ __forceinline__ void dp_wait(const DpParams& prm, int phase) {
   const int t = threadIdx.x;
   if (t < prm.world) {
     const uint32_t* mine = prm.ctrl[prm.rank] + phase * kMaxRanks + t;
-    while (ld_acquire_sys(mine) != prm.epoch) { __nanosleep(40); }
+    while (ld_acquire_sys(mine) != prm.epoch) { __nanosleep(20); }
   }
   __syncthreads();
 }
@@ -245,8 +245,7 @@ dp_apply_kernel(const __grid_constant__ DpParams prm) {
   }
   const double part = block_reduce_to_double(acc, red);
   if (threadIdx.x == 0) prm.partials[blockIdx.x] = part;
-  __threadfence_system();          // my a' stores (read by nobody else) and partial are out
-  grid.sync();
+  grid.sync();                     // gpu-scope: a' (local, read only by this rank) and the partials are visible
 
   // ---- flag 1: this rank's partial norm goes to every rank (itself included) ---------------------
   if (blockIdx.x == 0) {

@@ -134,3 +134,56 @@ def test_nan_gradient_propagates():
     op.run(grads)
     assert all(torch.isnan(t).all() for t in tp)
     assert torch.isnan(op.m_view(1)).all() and (op.accum == 0).all()
+
+
+def test_split_branches_equal_fused_step():
+    """accumulate_only + apply_only(None) (what the data-parallel drivers call) == run() on the apply step."""
+    import gaccum_b200 as g
+    from gaccum_b200.train_op import GaccumTrainOp
+    rng = np.random.default_rng(11)
+    params = make_params(TOY, rng)
+    names = [n for n, _ in TOY]
+    mk = lambda: GaccumTrainOp([torch.from_numpy(p.copy()).cuda() for p in params], names, g.HParams.bert(), 3, lambda s: 2e-3)
+    a, b = mk(), mk()
+    for step in range(7):
+        grads = [torch.from_numpy(x).cuda() for x in make_grads(TOY, 0.7, 0, step)]
+        a.run(grads)
+        if b.global_step % b.N == 0:
+            b.accumulate_only(grads)
+            b.apply_only(None)
+            b.global_step += 1
+        else:
+            b.run(grads)
+        for x, y in zip(a.params, b.params):
+            assert torch.equal(x, y)
+        assert torch.equal(a.m, b.m) and torch.equal(a.v, b.v) and torch.equal(a.accum, b.accum)
+        assert a.stats() == b.stats() or not a.last_applied
+
+
+def test_empty_single_element_and_full_pointer_table():
+    """Edge shapes: a zero-size tensor, 1-element tensors, and T = 1920 (the largest pointer table)."""
+    import gaccum_b200 as g
+    from gaccum_b200.train_op import GaccumTrainOp
+    rng = np.random.default_rng(12)
+    man = [("empty/kernel", (0,)), ("one/kernel", (1,)), ("one/bias", (1,))]
+    man += [(f"t{i}/{'bias' if i % 3 == 0 else 'kernel'}", (int(rng.integers(1, 70)),)) for i in range(1917)]
+    assert len(man) == 1920
+    params = [rng.normal(0, 0.02, s).astype(np.float32) for _, s in man]
+    ref = oracle_for(man, params, onp.HParams.bert(), 2, constant_lr=1e-4)
+    flat = torch.zeros(sum(p.size for p in params) + 8, device="cuda")
+    tp, o = [], 0
+    for p in params:                          # views into one flat buffer: arbitrary 4-byte alignment
+        t = flat[o:o + p.size]; t.copy_(torch.from_numpy(p)); tp.append(t); o += p.size
+    op = GaccumTrainOp(tp, [n for n, _ in man], g.HParams.bert(), 2, lambda s: 1e-4)
+    assert op.plan.T == 1920 and op.plan.num_tiles == 1919
+    for step in range(3):
+        grads = [rng.normal(0, 0.05, s).astype(np.float32) for _, s in man]
+        info = ref.run(grads)
+        gflat = torch.from_numpy(np.concatenate([x.ravel() for x in grads])).cuda()
+        tg, o = [], 0
+        for x in grads:
+            tg.append(gflat[o:o + x.size]); o += x.size
+        assert op.run(tg) == info.applied
+        _compare(op, tp, ref, bitexact=False)
+    with pytest.raises(g.GaccumError):
+        g.Plan([1] * 1921, None, g.HParams.bert(), device=0)
