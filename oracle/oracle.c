@@ -56,41 +56,41 @@ ORACLE_API float oracle_learning_rate(double init_lr, int64_t num_train_steps,
 
 /* ---- a6: assign_add, optimization.py:81,93 ---- */
 ORACLE_API void oracle_assign_add(float* a, const float* g, int64_t n) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n > 16384)
   for (int64_t i = 0; i < n; ++i) a[i] = a[i] + g[i];
 }
 
 /* un-fused elementwise helpers: each is one TF op with a materialised output */
 static void op_mul_s(float* o, float s, const float* x, int64_t n) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n > 16384)
   for (int64_t i = 0; i < n; ++i) o[i] = s * x[i];
 }
 static void op_div_s(float* o, const float* x, float s, int64_t n) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n > 16384)
   for (int64_t i = 0; i < n; ++i) o[i] = x[i] / s;
 }
 static void op_add(float* o, const float* x, const float* y, int64_t n) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n > 16384)
   for (int64_t i = 0; i < n; ++i) o[i] = x[i] + y[i];
 }
 static void op_sub(float* o, const float* x, const float* y, int64_t n) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n > 16384)
   for (int64_t i = 0; i < n; ++i) o[i] = x[i] - y[i];
 }
 static void op_mul(float* o, const float* x, const float* y, int64_t n) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n > 16384)
   for (int64_t i = 0; i < n; ++i) o[i] = x[i] * y[i];
 }
 static void op_div(float* o, const float* x, const float* y, int64_t n) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n > 16384)
   for (int64_t i = 0; i < n; ++i) o[i] = x[i] / y[i];
 }
 static void op_sqrt(float* o, const float* x, int64_t n) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n > 16384)
   for (int64_t i = 0; i < n; ++i) o[i] = sqrtf(x[i]);
 }
 static void op_add_s(float* o, const float* x, float s, int64_t n) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n > 16384)
   for (int64_t i = 0; i < n; ++i) o[i] = x[i] + s;
 }
 
@@ -100,7 +100,7 @@ static void op_add_s(float* o, const float* x, float s, int64_t n) {
 ORACLE_API float oracle_l2_loss(const float* x, int64_t n) {
   int64_t nb = (n + L2_BLOCK - 1) / L2_BLOCK;
   double* part = (double*)malloc(sizeof(double) * (size_t)(nb > 0 ? nb : 1));
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n > 16384)
   for (int64_t b = 0; b < nb; ++b) {
     int64_t lo = b * L2_BLOCK, hi = lo + L2_BLOCK < n ? lo + L2_BLOCK : n;
     double s = 0.0;
