@@ -219,3 +219,41 @@ def test_example_script_trains():
     assert out.returncode == 0, out.stderr[-2000:]
     losses = [float(l.split("loss")[1]) for l in out.stdout.splitlines() if "loss" in l]
     assert len(losses) >= 3 and losses[-1] < 0.5 * losses[0], out.stdout
+
+
+def test_estimator_contract_train_eval_and_midwindow_resume(tmp_path):
+    """model_fn -> EstimatorSpec(train_op) -> Estimator.train/evaluate; checkpoint mid-window and resume
+    bit-exactly (the reference gets this from the Saver seeing accum/adam_m/adam_v/global_step)."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "examples"))
+    import importlib
+    from gaccum_b200 import estimator as est, graph
+    ex = importlib.import_module("02_single_worker_with_estimator_gaccum")
+    hp = {'learning_rate': 1e-3, 'batch_size': 64, 'gradient_accumulation_multiplier': 4}
+    # uninterrupted: 10 micro-steps
+    a = est.Estimator(ex.model_fn, est.RunConfig(tf_random_seed=5, log_step_count_steps=0), hp)
+    a.train(ex.input_fn("train", 10, 64))
+    pa = [v.tensor.detach().clone() for v in graph.trainable_variables()]
+    # interrupted after 6 (mid-window: 6 % 4 == 2) and resumed from the checkpoint
+    d = str(tmp_path / "ckpt")
+    b1 = est.Estimator(ex.model_fn, est.RunConfig(model_dir=d, tf_random_seed=5, log_step_count_steps=0), hp)
+    b1.train(ex.input_fn("train", 6, 64))
+    assert os.path.exists(os.path.join(d, "model.ckpt.pt"))
+    saved = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in b1._spec.train_op.engine.state_dict().items()}
+    assert any(float(v.abs().max()) > 0 for k, v in saved.items() if k.endswith("/accum_grad"))   # really mid-window
+    b2 = est.Estimator(ex.model_fn, est.RunConfig(model_dir=d, tf_random_seed=99, log_step_count_steps=0), hp)
+    b2._build(est.ModeKeys.TRAIN)                       # different init seed: everything must come from the checkpoint
+    restored = b2._spec.train_op.engine.state_dict()
+    assert set(restored) == set(saved) and int(restored["global_step"]) == 6
+    for k, v in saved.items():
+        assert torch.equal(torch.as_tensor(v).cpu(), torch.as_tensor(restored[k]).cpu()), k   # bit-exact state, incl. beta powers
+    b2.train(ex.input_fn("train", 4, 64, start=6))
+    assert int(graph.get_global_step()) == 10
+    for x, v in zip(pa, graph.trainable_variables()):    # cuDNN's conv backward is not bit-reproducible run to run
+        assert torch.allclose(x, v.tensor, rtol=1e-4, atol=1e-6), v.name
+    # and it learns: train longer, evaluate
+    c = est.Estimator(ex.model_fn, est.RunConfig(tf_random_seed=5, log_step_count_steps=50), hp)
+    res = est.train_and_evaluate(c, ex.input_fn("train", 400, 64), ex.input_fn("eval", 5, 512, seed=1))
+    assert res["accuracy"] > 0.9 and res["global_step"] == 400 and len(c.log) == 8
