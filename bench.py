@@ -41,9 +41,8 @@ INIT_LR, TRAIN_STEPS, WARMUP_STEPS = 2e-5, 207900, 20790      # reference README
 
 
 def manifest(name):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle_np
-    return oracle_np.MANIFESTS[WORKLOADS[name][0]]()
+    from gaccum_b200.manifests import MANIFESTS       # the product's own shape tables (never the oracle's)
+    return MANIFESTS[WORKLOADS[name][0]]()
 
 
 def measured_traffic(workload):
@@ -127,7 +126,7 @@ def cpu_reference(workload: str, accum_n: int, budget_s: float, variant_b: bool)
     import numpy as np
     import oracle_c
     import oracle_np as onp
-    man = manifest(workload)
+    man = onp.MANIFESTS[WORKLOADS[workload][0]]()       # the CPU leg stands on the oracle alone
     rng = np.random.default_rng(19830610)
     params = [rng.normal(0, 0.02, s).astype(np.float32) for _, s in man]
     hp = onp.HParams.tf_adam() if variant_b else onp.HParams.bert()
@@ -179,7 +178,8 @@ def run_reference_arm(args):
     N = args.accum_n or WORKLOADS[wl][1]
     t0 = time.perf_counter()
     rate, info, med = cpu_reference(wl, N, budget_s=min(60.0, 0.05 * max(args.steps, 1) + 10.0), variant_b=(wl == "mnist_cnn"))
-    man = manifest(wl)
+    import oracle_np
+    man = oracle_np.MANIFESTS[WORKLOADS[wl][0]]()
     out = {"impl": "reference", "metric": "micro-steps/sec (train_op only, CPU reference path)", "value": rate,
            "unit": "micro-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": 1e3 / rate, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

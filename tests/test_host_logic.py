@@ -134,3 +134,28 @@ def test_create_optimizer_signature_and_tpu_rejection():
     o = opt.AdamWeightDecayOptimizer(1e-3, weight_decay_rate=0.01, exclude_from_weight_decay=["LayerNorm", "bias"])
     assert o._get_variable_name("a/b:0") == "a/b" and o._get_variable_name("a/b") == "a/b"
     assert o._do_use_weight_decay("x/kernel") and not o._do_use_weight_decay("x/bias") and not o._do_use_weight_decay("LayerNorm/g")
+
+
+def test_product_manifests_match_the_oracles_and_the_survey():
+    """bench.py takes shapes from the package, the tests from the oracle: they must be the same tables."""
+    from gaccum_b200.manifests import MANIFESTS
+    assert set(MANIFESTS) == set(onp.MANIFESTS)
+    for k in MANIFESTS:
+        assert MANIFESTS[k]() == onp.MANIFESTS[k]()
+    assert len(MANIFESTS["bert_base"]()) == 201 and len(MANIFESTS["bert_large"]()) == 393
+
+
+def test_oracle_is_not_imported_by_the_product():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/."""
+    import subprocess, sys
+    code = ("import sys, gaccum_b200, gaccum_b200.optimization, gaccum_b200.graph, gaccum_b200.manifests, "
+            "gaccum_b200.estimator, gaccum_b200.distributed, gaccum_b200.train_op; "
+            "bad=[m for m in sys.modules if m.startswith('oracle')]; print(bad); sys.exit(1 if bad else 0)")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for rel in ("gradient-accumulation-tf-estimator_b200", "include", "examples"):
+        for dp, _, files in os.walk(os.path.join(ROOT, rel)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cc")):
+                    txt = open(os.path.join(dp, f), errors="ignore").read()
+                    assert "import oracle" not in txt and "oracle_np" not in txt and "liboracle" not in txt, os.path.join(dp, f)

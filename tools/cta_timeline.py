@@ -2,12 +2,13 @@
 """Per-CTA timeline of the clip-apply kernel (GACCUM_EXPERIMENTS=1): where does each CTA wait?"""
 import ctypes as C, os, sys
 os.environ["GACCUM_EXPERIMENTS"] = "1"
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.join(sys.path[0], "oracle"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-import gaccum_b200 as g, oracle_np as onp
+import gaccum_b200 as g
+from gaccum_b200.manifests import MANIFESTS
 from gaccum_b200.train_op import GaccumTrainOp
 from gaccum_b200 import _lib
-man = onp.MANIFESTS["bert_small"]()
+man = MANIFESTS["bert_small"]()
 dev = torch.device("cuda:0")
 sets = []
 for r in range(3):
