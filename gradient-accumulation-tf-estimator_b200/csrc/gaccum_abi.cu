@@ -432,7 +432,7 @@ int gaccum_plan_create(gaccum_plan** out, int32_t T, const int64_t* numels, cons
   // measured best on B200 (profiles/r01_tune_sweep.md): evict_last a', streaming state, tile-per-CTA
   // accumulate, shared-memory + Tensor-Memory stash of a'.  GACCUM_TUNE overrides for A/B sweeps; the
   // bits that skip work (timing decomposition, WRONG results) additionally need GACCUM_EXPERIMENTS=1.
-  pl->tune = kTuneKeepA | kTuneStreamState | kTuneAccTiles | kTuneStaticApply | kTuneTmemStash;
+  pl->tune = kTuneKeepA | kTuneStreamState | kTuneAccTiles | kTuneStaticApply | kTuneTmemStash | kTunePrefetch;
   if (const char* t = getenv("GACCUM_TUNE")) pl->tune = (uint32_t)strtoul(t, nullptr, 0);
   if ((pl->tune & (kTuneSkipPass1 | kTuneSkipPass2 | kTuneSkipZero)) && !getenv("GACCUM_EXPERIMENTS")) {
     delete pl;

@@ -96,6 +96,8 @@ constexpr uint32_t kTuneSkipPass2 = 32u;   // TIMING EXPERIMENTS ONLY: skip the 
 constexpr uint32_t kTuneOwnBarrier = 128u;  // clip-apply v2: ordinary launch + atomic grid barrier (no cooperative launch)
 constexpr uint32_t kTuneApplyV1 = 256u;     // clip-apply: use the first two-pass kernel (no on-chip stash)
 constexpr uint32_t kTuneTmemStash = 512u;   // clip-apply v2: also park a' tiles in Tensor Memory (tcgen05.st / tcgen05.ld)
+constexpr uint32_t kTunePrefetch = 1024u;   // clip-apply v2: L2 software prefetch of the next tiles in pass 1
+constexpr int kPrefetchDistance = 1;        // iterations ahead
 constexpr uint32_t kTuneSkipZero = 64u;    // TIMING EXPERIMENTS ONLY (dp kernel): skip zeroing non-owned tiles
 
 // ---------------------------------------------------------------------------------------------
@@ -559,6 +561,21 @@ struct NormRegs {
   bool vec;          // false: unaligned gradient pointer -> scalar path, nothing was loaded
 };
 
+// Software prefetch into L2 of a tile the group will reduce one iteration later: prefetch.global.L2
+// needs no destination registers, so it adds bytes in flight without adding register pressure (the
+// thing that kept the 24-warp pass 1 latency-bound).  Threads 0..63 cover the 64 lines of `a`,
+// threads 64..127 those of G.
+template <bool HAS_G, int CAP>
+__device__ __forceinline__ void norm_prefetch(const TileDesc& d, const KernelParams<CAP>& prm) {
+  const uint32_t tid = threadIdx.x & (kThreads - 1);
+  const uint32_t line = tid & 63u;
+  if (line * 32u >= d.len) return;
+  const float* ptr = nullptr;
+  if (tid < 64) ptr = prm.accum + (size_t)d.soff32 * kSlabAlign;
+  else if (tid < 128) { if constexpr (HAS_G) ptr = grad_ptr(prm.tab, d); }
+  if (ptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + line * 32u));
+}
+
 template <bool HAS_G, int CAP>
 __device__ __forceinline__ void norm_issue(const TileDesc& d, const KernelParams<CAP>& prm, const bool on_chip,
                                            const uint64_t pol, NormRegs& r) {
@@ -750,6 +767,13 @@ apply_clip2_kernel(const __grid_constant__ KernelParams<CAP> prm) {
         st[j] = (k < n_stashed && stashable<HAS_G>(d[j], prm)) ? stash_mem + (size_t)k * (kTile / 4) : nullptr;
         tm[j] = st[j] ? kNoTmem : tmem_for(k, d[j]);
         norm_issue<HAS_G>(d[j], prm, st[j] != nullptr || tm[j] != kNoTmem, pol, r[j]);
+      }
+    }
+    if (prm.tune & kTunePrefetch) {
+#pragma unroll
+      for (int j = 0; j < kPass1Tiles; ++j) {
+        const int k = k0 + kPass1Tiles * kPrefetchDistance + j;
+        if (k < my_count) norm_prefetch<HAS_G>(prm.tiles[b + k * G], prm);
       }
     }
 #pragma unroll

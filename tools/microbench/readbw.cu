@@ -1,6 +1,7 @@
 // Read-only vs copy HBM bandwidth on B200: what is the roofline of a pass that only READS?
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o readbw readbw.cu
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 template <int MODE>
 __global__ void __launch_bounds__(256) rd(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ c, size_t n, float* out) {
@@ -14,10 +15,12 @@ __global__ void __launch_bounds__(256) rd(const float4* __restrict__ a, const fl
   }
   if (MODE == 0 && acc == 123.456f) *out = acc;
 }
-int main() {
-  const size_t n = (size_t)64 << 20;   // 64 Mi float4 = 1 GiB per array
+int main(int argc, char** argv) {
+  // default: 64 Mi float4 = 1 GiB per array; pass a float4 count to mimic a short pass
+  // (BERT-Small pass 1 reads 2 x 115 MB: ./readbw 7191168)
+  const size_t n = argc > 1 ? (size_t)atoll(argv[1]) : (size_t)64 << 20;
   float4 *a, *b, *c; float* out;
-  cudaMalloc(&a, n * 16); cudaMalloc(&b, n * 16); cudaMalloc(&c, n * 16); cudaMalloc(&out, 4);
+  cudaMalloc(&a, n * 16); cudaMalloc(&b, n * 16); cudaMalloc(&c, n * 16 > ((size_t)512 << 20) ? n * 16 : ((size_t)512 << 20)); cudaMalloc(&out, 4);
   cudaMemset(a, 0, n * 16); cudaMemset(b, 0, n * 16);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int mode = 0; mode < 2; ++mode)
@@ -25,6 +28,7 @@ int main() {
       int grid = 148 * per_sm;
       float best = 1e9;
       for (int it = 0; it < 6; ++it) {
+        if (n < ((size_t)16 << 20)) cudaMemsetAsync(c, 0, 512u << 20);   // evict a and b from L2 (c is >= 512 MB only when n is large: guard below)
         cudaEventRecord(e0);
         if (mode == 0) rd<0><<<grid, 256>>>(a, b, c, n, out); else rd<1><<<grid, 256>>>(a, b, c, n, out);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
