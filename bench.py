@@ -177,7 +177,8 @@ def run_reference_arm(args):
     wl = args.workload
     N = args.accum_n or WORKLOADS[wl][1]
     t0 = time.perf_counter()
-    rate, info, med = cpu_reference(wl, N, budget_s=min(60.0, 0.05 * max(args.steps, 1) + 10.0), variant_b=(wl == "mnist_cnn"))
+    budget = args.cpu_budget if args.cpu_budget_given else min(60.0, 0.05 * max(args.steps, 1) + 10.0)
+    rate, info, med = cpu_reference(wl, N, budget_s=budget, variant_b=(wl == "mnist_cnn"))
     import oracle_np
     man = oracle_np.MANIFESTS[WORKLOADS[wl][0]]()
     out = {"impl": "reference", "metric": "micro-steps/sec (train_op only, CPU reference path)", "value": rate,
@@ -376,8 +377,19 @@ def run_b200_arm(args):
     if with_model:
         out["with_model"] = with_model
     if world == 1 and args.cpu_budget > 0:
-        _, info, _ = cpu_reference(wl, N, args.cpu_budget, variant_b)
-        out["cpu_baseline"] = info
+        # The CPU leg runs in a fresh interpreter: in this process PyTorch's bundled OpenMP runtime is
+        # already loaded (active spin-waiting, its own thread settings) and starves the oracle's loops.
+        import subprocess
+        env = dict(os.environ, OMP_WAIT_POLICY="PASSIVE")
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", wl, "--accum-n", str(N),
+               "--steps", str(K), "--warmup", str(W), "--cpu-budget", str(args.cpu_budget)]
+        try:
+            r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=args.cpu_budget * 6 + 120)
+            line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+            out["cpu_baseline"] = json.loads(line)["cpu_baseline"]
+        except Exception as e:       # never lose the GPU line because the CPU leg failed
+            out["cpu_baseline"] = {"value": None, "unit": "micro-steps/s", "cores": None, "kind": "port",
+                                   "sample": f"CPU leg failed: {type(e).__name__}: {e}"}
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
@@ -458,6 +470,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=48)
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-oracle timing (0 disables)")
     args = ap.parse_args()
+    args.cpu_budget_given = any(a.startswith("--cpu-budget") for a in sys.argv[1:])
     if args.impl == "reference":
         run_reference_arm(args)
     else:
