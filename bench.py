@@ -304,8 +304,21 @@ def run_b200_arm(args):
     e2e = None
     if args.e2e_steps > 0:
         from gaccum_b200.train_op import HostTrainOp
+        # allocate (first-touch) the pinned host buffers on the NUMA node next to this GPU, as a
+        # NUMA-aware host framework would: bind to the GPU's ideal CPUs while allocating
+        old_aff, numa = None, "default placement"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            old_aff = os.sched_getaffinity(0)
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+            numa = f"pinned buffers first-touched on the GPU-local CPUs ({len(os.sched_getaffinity(0))} of {len(old_aff)})"
+        except Exception:
+            old_aff = None
         host_params = [(torch.randn(s) * 0.02).pin_memory() for _, s in man]
         host_grads = [[torch.randn(s).mul_(args.sigma).pin_memory() for _, s in man] for _ in range(2)]
+        if old_aff is not None and not args.e2e_keep_affinity:
+            os.sched_setaffinity(0, old_aff)
         hop = HostTrainOp(host_params, names, hp, N, lr_fn, global_step=100001, device=local)
         hb = [hop.bind(hg) for hg in host_grads]
         Ke = args.e2e_steps
@@ -327,6 +340,7 @@ def run_b200_arm(args):
         e2e = {"value": world * Ke / (ms * 1e-3), "unit": "micro-steps/s",
                "h2d_bytes_per_step": 4 * P, "d2h_bytes_per_step": int(4 * P * napply / Ke) + 16,
                "steps": Ke, "ms_per_step": ms / Ke, "api": "gaccum_step_host (C ABI) via HostTrainOp.run_bound",
+               "host_memory": numa,
                "note": "pinned host gradients H2D every micro-step; stats D2H every step; parameters D2H on apply steps; "
                        "replicas are independent at N>1 (no exchange on this path)"}
         del hop
@@ -468,6 +482,7 @@ def main():
     ap.add_argument("--no-clip", action="store_true", help="experiment: AdamWeightDecay without clip_by_global_norm (single-pass apply)")
     ap.add_argument("--model-steps", type=int, default=48, help="micro-steps of the with-model leg (0 disables)")
     ap.add_argument("--e2e-steps", type=int, default=48)
+    ap.add_argument("--e2e-keep-affinity", action="store_true", help="experiment: keep the GPU-local CPU affinity for the whole e2e leg")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-oracle timing (0 disables)")
     args = ap.parse_args()
     args.cpu_budget_given = any(a.startswith("--cpu-budget") for a in sys.argv[1:])
