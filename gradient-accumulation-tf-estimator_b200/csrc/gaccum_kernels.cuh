@@ -1,23 +1,31 @@
 // gaccum_kernels.cuh -- sm_100a kernels of the gradient-accumulation train_op.
 //
-// Two kernels, both persistent (grid = SMs x resident CTAs) and grid-striding over a static
-// tile table, so the work split -- and therefore every reduction -- is deterministic:
+// All kernels grid-stride over a static tile table (<= 2048 elements of one tensor per tile), so the
+// work split -- and therefore every reduction -- is deterministic.
 //
-//   accumulate_kernel   a += G                                   optimization.py:81,93   (12 B/elem)
-//   apply_kernel        a' = a + G; n = a'/N; [gn = ||n||; s = clip scale; c = n*s];
-//                       AdamWeightDecay | Adam update of p, m, v; a = 0
-//                                                 optimization.py:80-88, 128-177        (36 B/elem)
-//
-// The apply kernel needs the global norm of ALL tensors before it can update ANY element, so
-// with clipping on it is a cooperative launch with two passes separated by one grid barrier:
-//   pass 1 streams G and a, writes a' back in place and reduces sum(n^2)
-//          (thread fp32 -> warp shuffle -> shared memory -> one fp64 partial per CTA);
-//   barrier; every CTA sums the per-CTA partials in the same fixed order (bit-identical s);
-//   pass 2 walks the CTA's tiles in REVERSE order, so the a' lines written last in pass 1 are
-//          read first and are served from the 126 MB L2 instead of HBM.
-// Arithmetic uses round-to-nearest intrinsics (__fmul_rn, __fadd_rn, __fdiv_rn, __fsqrt_rn)
-// so nvcc cannot contract mul+add into FMA: the reference graph is un-fused, one rounding per
-// TF op, and we reproduce it bit for bit (the kernel is HBM-bound, the extra flops are free).
+//   accumulate_kernel    a += G                                  optimization.py:81,93    (12 B/elem)
+//                        one tile per CTA (hardware block scheduler)
+//   apply_kernel         the apply branch WITHOUT clipping (plain Adam of the example scripts, or
+//                        clip_norm <= 0): a' = a + G; n = a'/N; Adam; a = 0 in a single pass (36 B/elem).
+//                        Its CLIP=true instantiation is the first two-pass version, kept behind
+//                        GACCUM_TUNE for A/B runs.
+//   apply_clip2_kernel   the apply branch WITH tf.clip_by_global_norm                  (36 B/elem)
+//                        optimization.py:80-88, 128-177.  The global norm of ALL tensors is needed before
+//                        ANY element can be updated, so it is one cooperative launch with two passes
+//                        around a grid barrier:
+//                          pass 1  stream G and a, a' = a + G, reduce sum((a'/N)^2)
+//                                  (thread fp32 per tile -> fp64 running sum -> warp shuffle -> shared
+//                                  memory -> one fp64 partial per CTA); a' is PARKED ON CHIP: oldest
+//                                  tiles in shared memory, next in Tensor Memory (tcgen05.st), the rest
+//                                  written back in place tagged L2::evict_last
+//                          barrier every CTA adds the per-CTA partials in the same order
+//                                  (bit-identical gn and clip scale everywhere)
+//                          pass 2  tiles in REVERSE order (youngest a' lines are still in L2, the oldest
+//                                  never left the SM): clip, AdamWeightDecay/Adam, write p, m, v, a = 0
+// Arithmetic uses round-to-nearest intrinsics (__fmul_rn, __fadd_rn, __fdiv_rn, __fsqrt_rn) so nvcc
+// cannot contract mul+add into FMA: the reference graph is un-fused, one rounding per TF op, and we
+// reproduce it bit for bit (the kernels are HBM-bound, the extra flops are free).
+// Measurements and the experiments behind each choice: profiles/r01_tune_sweep.md.
 #pragma once
 
 #include <cooperative_groups.h>
