@@ -79,7 +79,12 @@ __device__ __forceinline__ void dp_wait(const DpParams& prm, int phase) {
   const int t = threadIdx.x;
   if (t < prm.world) {
     const uint32_t* mine = prm.ctrl[prm.rank] + phase * kMaxRanks + t;
-    while (ld_acquire_sys(mine) != prm.epoch) { __nanosleep(20); }
+    // poll with relaxed loads (no fence per probe), acquire once when the flag has flipped
+    uint32_t seen;
+    do {
+      asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+    } while (seen != prm.epoch);
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
   }
   __syncthreads();
 }
