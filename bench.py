@@ -38,6 +38,18 @@ WORKLOADS = {
     "bert_large": ("bert_large", 32, "BERT-Large L24_H1024_A16 seq512 micro_bs4 accum x32"),
 }
 INIT_LR, TRAIN_STEPS, WARMUP_STEPS = 2e-5, 207900, 20790      # reference README.md:72,75
+START_STEP = 100003      # steady state, mid-schedule; 100004 % {4,8,32} == 4 % N: the first apply comes early for N=4
+
+
+def _finite(x):
+    """JSON has no NaN/Infinity: a leg that saw no launch of a kind reports null instead."""
+    if isinstance(x, float):
+        return x if x == x and abs(x) != float("inf") else None
+    if isinstance(x, dict):
+        return {k: _finite(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_finite(v) for v in x]
+    return x
 
 
 def manifest(name):
@@ -190,7 +202,7 @@ def run_reference_arm(args):
            "cpu_baseline": info,
            "e2e": {"value": rate, "unit": "micro-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
-    print(json.dumps(out))
+    print(json.dumps(_finite(out)))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -236,10 +248,12 @@ def run_b200_arm(args):
         dp = None
         if world > 1 and args.dp == "fused":
             from gaccum_b200.distributed import FusedDataParallelTrainOp
-            dp = FusedDataParallelTrainOp(params, names, hp, N, lr_fn, global_step=100001)
+            dp = FusedDataParallelTrainOp(params, names, hp, N, lr_fn, global_step=START_STEP + r)
             op = dp.engine
         else:
-            op = GaccumTrainOp(params, names, hp, N, lr_fn, global_step=100001)   # steady state, mid-schedule
+            # steady state, mid-schedule; the sets are staggered by one micro-step so that any run of
+            # consecutive timed steps contains accumulate and apply launches in the 1 : N-1 proportion
+            op = GaccumTrainOp(params, names, hp, N, lr_fn, global_step=START_STEP + r)
         op.m.normal_(0, 1e-4, generator=gen); op.v.uniform_(0, 1e-8, generator=gen)
         grads = [[torch.randn(s, device=dev, generator=gen) * args.sigma for _, s in man] for _ in range(NG)]
         bound = [op.bind(gl) for gl in grads]      # what a graph-mode caller hands the op: raw pointers
@@ -319,7 +333,7 @@ def run_b200_arm(args):
         host_grads = [[torch.randn(s).mul_(args.sigma).pin_memory() for _, s in man] for _ in range(2)]
         if old_aff is not None and not args.e2e_keep_affinity:
             os.sched_setaffinity(0, old_aff)
-        hop = HostTrainOp(host_params, names, hp, N, lr_fn, global_step=100001, device=local)
+        hop = HostTrainOp(host_params, names, hp, N, lr_fn, global_step=START_STEP, device=local)
         hb = [hop.bind(hg) for hg in host_grads]
         Ke = args.e2e_steps
         for i in range(4):
@@ -404,7 +418,7 @@ def run_b200_arm(args):
         except Exception as e:       # never lose the GPU line because the CPU leg failed
             out["cpu_baseline"] = {"value": None, "unit": "micro-steps/s", "cores": None, "kind": "port",
                                    "sample": f"CPU leg failed: {type(e).__name__}: {e}"}
-    print(json.dumps(out))
+    print(json.dumps(_finite(out)))
     if dist is not None:
         dist.destroy_process_group()
 
