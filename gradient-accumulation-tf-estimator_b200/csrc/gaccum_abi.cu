@@ -309,10 +309,11 @@ struct DeviceGuard {
 
 template <int CAP>
 static int do_accumulate_tab(gaccum_plan* pl, const float* const* grads, float* accum,
-                             const gaccum_step_args* a, cudaStream_t st) {
+                             const gaccum_step_args* a, cudaStream_t st, uint32_t extra_tune = 0) {
   KernelParams<CAP>* prm = new (std::nothrow) KernelParams<CAP>();
   if (!prm) return fail(GACCUM_ENOMEM, "out of host memory");
   fill_common(pl, *prm, accum, nullptr, nullptr, make_scalars(pl->hp, a));
+  prm->tune |= extra_tune;
   int rc = fill_table(pl, prm->tab, grads, nullptr);
   if (rc == GACCUM_OK) rc = launch_accumulate(pl, *prm, st);
   delete prm;
@@ -645,7 +646,60 @@ struct gaccum_host_session {
   cudaStream_t compute = nullptr, h2d = nullptr, d2h = nullptr;
   cudaEvent_t buf_free[2] = {nullptr, nullptr}, h2d_done[2] = {nullptr, nullptr}, k_done = nullptr, d2h_done = nullptr;
   uint64_t calls = 0;
+  // zero-copy path: pinned (device-mapped) host gradients are read by the kernel itself over PCIe
+  std::vector<const float*> last_host, dev_alias;
+  std::vector<float*> param_ptrs;
+  bool last_direct = false, force_staged = false, gather_small = false;
+  // staged path: tensors below kGatherBytes are gathered by ONE kernel from pinned host memory instead
+  // of one cudaMemcpyAsync each (46 of BERT-Small's 73 tensors are <= 2 KB; a copy costs ~6 us of gap)
+  std::vector<const float*> g_last, g_alias;
+  bool g_ok = false;
 };
+constexpr size_t kGatherBytes = 256 * 1024;
+
+static bool resolve_gather(gaccum_host_session* s, const float* const* host_grads) {
+  gaccum_plan* pl = s->plan;
+  if (!s->gather_small) return false;
+  bool same = (int)s->g_last.size() == pl->T;
+  for (int32_t t = 0; same && t < pl->T; ++t) same = s->g_last[t] == host_grads[t];
+  if (same) return s->g_ok;
+  s->g_last.assign(host_grads, host_grads + pl->T);
+  s->g_alias.assign((size_t)pl->T, nullptr);
+  bool ok = true, any = false;
+  for (int32_t t = 0; t < pl->T && ok; ++t) {
+    if (!host_grads[t] || pl->numel[t] == 0 || (size_t)pl->numel[t] * sizeof(float) > kGatherBytes) continue;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, host_grads[t]) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+    if (at.type != cudaMemoryTypeHost || at.devicePointer == nullptr) { ok = false; break; }
+    s->g_alias[t] = static_cast<const float*>(at.devicePointer);
+    any = true;
+  }
+  s->g_ok = ok && any;
+  return s->g_ok;
+}
+
+// Are all gradient buffers pinned host memory the device can address (UVA)?  Then the kernels can
+// consume them in place: no staging copy, no 73 cudaMemcpyAsync per micro-step (each costs ~6 us of
+// copy-engine gap), one PCIe-bound kernel.  Cached on the pointer set.
+static bool resolve_direct(gaccum_host_session* s, const float* const* host_grads) {
+  gaccum_plan* pl = s->plan;
+  if (s->force_staged) return false;
+  bool same = (int)s->last_host.size() == pl->T;
+  for (int32_t t = 0; same && t < pl->T; ++t) same = s->last_host[t] == host_grads[t];
+  if (same) return s->last_direct;
+  s->last_host.assign(host_grads, host_grads + pl->T);
+  s->dev_alias.assign((size_t)pl->T, nullptr);
+  bool direct = true;
+  for (int32_t t = 0; t < pl->T && direct; ++t) {
+    if (!host_grads[t] || pl->numel[t] == 0) continue;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, host_grads[t]) != cudaSuccess) { cudaGetLastError(); direct = false; break; }
+    if (at.type != cudaMemoryTypeHost || at.devicePointer == nullptr) { direct = false; break; }
+    s->dev_alias[t] = static_cast<const float*>(at.devicePointer);
+  }
+  s->last_direct = direct;
+  return direct;
+}
 
 int gaccum_host_session_destroy(gaccum_host_session* s) {
   if (!s) return GACCUM_OK;
@@ -693,6 +747,12 @@ int gaccum_host_session_create(gaccum_host_session** out, gaccum_plan* pl) {
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->k_done, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->d2h_done, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  s->param_ptrs.resize((size_t)pl->T);
+  for (int32_t t = 0; t < pl->T; ++t) s->param_ptrs[t] = s->d_params + pl->offset[t];
+  // measured on B200 / PCIe Gen5 (profiles/r01_tune_sweep.md): the copy engines move the large tensors
+  // faster (55 GB/s) than SM loads over PCIe (41 GB/s), so the zero-copy path is opt-in
+  s->force_staged = getenv("GACCUM_HOST_DIRECT") == nullptr;
+  s->gather_small = getenv("GACCUM_HOST_GATHER") != nullptr;   // gathering the small tensors with one kernel: no gain measured, opt-in
   if (e != cudaSuccess) {
     gaccum_host_session_destroy(s);
     return fail(GACCUM_ECUDA, "host session setup failed: %s", cudaGetErrorString(e));
@@ -721,16 +781,54 @@ int gaccum_step_host(gaccum_host_session* s, const float* const* host_grads, flo
   if (int rc = check_args(a)) return rc;
   gaccum_plan* pl = s->plan;
   DeviceGuard guard(pl->device);
+  const bool apply_step = gaccum_is_apply_step(a->global_step, a->accum_n) != 0;
+  if (resolve_direct(s, host_grads)) {
+    // ---- zero-copy: the kernel streams the gradients out of pinned host memory ------------------
+    cudaStream_t st = s->compute;
+    int rc;
+    if (apply_step) {
+      rc = pl->T <= kCapSmall
+               ? do_apply_tab<kCapSmall>(pl, s->dev_alias.data(), s->param_ptrs.data(), s->d_accum, s->d_m, s->d_v, a, st)
+               : do_apply_tab<kCapLarge>(pl, s->dev_alias.data(), s->param_ptrs.data(), s->d_accum, s->d_m, s->d_v, a, st);
+    } else {
+      rc = pl->T <= kCapSmall ? do_accumulate_tab<kCapSmall>(pl, s->dev_alias.data(), s->d_accum, a, st)
+                              : do_accumulate_tab<kCapLarge>(pl, s->dev_alias.data(), s->d_accum, a, st);
+    }
+    if (rc) return rc;
+    ++s->calls;
+    if (stats_out)
+      CUDA_TRY(cudaMemcpyAsync(stats_out, pl->d_stats, sizeof(gaccum_stats), cudaMemcpyDeviceToHost, s->compute));
+    if (apply_step && host_params_out) {
+      CUDA_TRY(cudaEventRecord(s->k_done, s->compute));
+      CUDA_TRY(cudaStreamWaitEvent(s->d2h, s->k_done, 0));
+      for (int32_t t = 0; t < pl->T; ++t) {
+        if (pl->numel[t] == 0 || !host_params_out[t]) continue;
+        CUDA_TRY(cudaMemcpyAsync(host_params_out[t], s->d_params + pl->offset[t], (size_t)pl->numel[t] * sizeof(float),
+                                 cudaMemcpyDeviceToHost, s->d2h));
+      }
+      CUDA_TRY(cudaEventRecord(s->d2h_done, s->d2h));
+      CUDA_TRY(cudaStreamWaitEvent(s->compute, s->d2h_done, 0));
+    }
+    return GACCUM_OK;
+  }
   const int b = (int)(s->calls & 1);
   ++s->calls;
   // H2D of this step's gradients into staging buffer b, once the kernel that last read it is done
   CUDA_TRY(cudaStreamWaitEvent(s->h2d, s->buf_free[b], 0));
   bool any_null = false;
+  const bool gather = resolve_gather(s, host_grads);
   for (int32_t t = 0; t < pl->T; ++t) {
     if (pl->numel[t] == 0) continue;
     if (!host_grads[t]) { any_null = true; continue; }
+    if (gather && s->g_alias[t]) continue;             // picked up by the gather kernel below
     CUDA_TRY(cudaMemcpyAsync(s->d_stage[b] + pl->offset[t], host_grads[t], (size_t)pl->numel[t] * sizeof(float),
                              cudaMemcpyHostToDevice, s->h2d));
+  }
+  if (gather) {                                        // one launch for all small tensors: stage = G_host
+    gaccum_step_args ga = *a;
+    int rc = pl->T <= kCapSmall ? do_accumulate_tab<kCapSmall>(pl, s->g_alias.data(), s->d_stage[b], &ga, s->h2d, kAccAssign)
+                                : do_accumulate_tab<kCapLarge>(pl, s->g_alias.data(), s->d_stage[b], &ga, s->h2d, kAccAssign);
+    if (rc) return rc;
   }
   if (any_null)   // tensors without a gradient contribute nothing (optimization.py:132): stage zeros
     for (int32_t t = 0; t < pl->T; ++t)

@@ -106,6 +106,7 @@ constexpr uint32_t kTuneApplyV1 = 256u;     // clip-apply: use the first two-pas
 constexpr uint32_t kTuneTmemStash = 512u;   // clip-apply v2: also park a' tiles in Tensor Memory (tcgen05.st / tcgen05.ld)
 constexpr uint32_t kTunePrefetch = 1024u;   // clip-apply v2: L2 software prefetch of the next tiles in pass 1
 constexpr int kPrefetchDistance = 1;        // iterations ahead
+constexpr uint32_t kAccAssign = 1u << 30;    // accumulate_kernel stores G instead of adding it (host-session gather of small tensors)
 constexpr uint32_t kTuneSkipZero = 64u;    // TIMING EXPERIMENTS ONLY (dp kernel): skip zeroing non-owned tiles
 
 // ---------------------------------------------------------------------------------------------
@@ -209,6 +210,10 @@ __device__ __forceinline__ void accumulate_tile(const TileDesc d, const KernelPa
   if (g == nullptr) return;   // optimization.py:132 -- tensors without a gradient are skipped
   float* __restrict__ a = prm.accum + (size_t)d.soff32 * kSlabAlign;
   const uint32_t len = d.len, tid = threadIdx.x;
+  if (prm.tune & kAccAssign) {              // gather: a = G (G may live in pinned host memory)
+    for (uint32_t i = tid; i < len; i += kThreads) a[i] = ld_stream(g + i);
+    return;
+  }
   if (aligned16(g)) {
     const uint32_t nvec = len >> 2;
     const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -239,7 +244,7 @@ template <int CAP>
 __global__ void __launch_bounds__(kThreads)
 accumulate_kernel(const __grid_constant__ KernelParams<CAP> prm) {
   int t = blockIdx.x;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && !(prm.tune & kAccAssign)) {   // the gather pass is not a step
     prm.stats[0] = 0.f; prm.stats[1] = prm.sc.lr; prm.stats[2] = 0.f; prm.stats[3] = 1.f;
   }
   if (t >= prm.num_tiles) return;
