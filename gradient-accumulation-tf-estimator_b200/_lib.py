@@ -59,6 +59,7 @@ _lib = None
 
 
 def lib_path() -> str:
+    _load()                 # make sure it exists (built on demand) before anyone dlopens the path
     return _build.LIB
 
 

@@ -16,7 +16,8 @@ def pytest_configure(config):
 @pytest.fixture(scope="session", autouse=True)
 def _built():
     """Both shared objects exist before any test runs (nvcc cross-compiles without a GPU)."""
-    import gaccum_b200  # noqa: F401  builds csrc/libgaccum.so if stale
+    import gaccum_b200
+    assert gaccum_b200.version() >= 100      # forces the (lazy) build + load of csrc/libgaccum.so
     import oracle_c
     oracle_c.build()
     yield
