@@ -35,6 +35,7 @@ constexpr int kMaxRanks = 8;
 constexpr int kCtrlFlagWords = 3 * kMaxRanks;
 constexpr int kCtrlNormByteOffset = 128;
 constexpr int kCtrlBytes = 256;
+constexpr unsigned long long kDpTimeoutNs = 60ull * 1000 * 1000 * 1000;   // a flag wait longer than 60 s is a dead peer
 
 struct DpParams {
   const TileDesc* tiles;
@@ -81,8 +82,18 @@ __device__ __forceinline__ void dp_wait(const DpParams& prm, int phase) {
     const uint32_t* mine = prm.ctrl[prm.rank] + phase * kMaxRanks + t;
     // poll with relaxed loads (no fence per probe), acquire once when the flag has flipped
     uint32_t seen;
+    unsigned long long t_start = 0;
+    uint32_t spins = 0;
     do {
       asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+      // A peer that never arrives (crashed rank, mismatched epoch) must not hang the GPU for ever:
+      // after kDpTimeoutNs the kernel traps, which surfaces as a sticky CUDA error on the host.
+      if (seen != prm.epoch && (++spins & 0x3fffu) == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t_start == 0) t_start = now;
+        else if (now - t_start > kDpTimeoutNs) __trap();
+      }
     } while (seen != prm.epoch);
     asm volatile("fence.acq_rel.sys;" ::: "memory");
   }

@@ -172,7 +172,9 @@ GACCUM_API int gaccum_dp_shard_range(const gaccum_plan* plan, int32_t world, int
                                      int32_t* tile_lo, int32_t* tile_hi, int64_t* num_elements);
 /* `epoch` must be non-zero and different from the previous call's (e.g. a call counter), and the
  * same on every rank.  m / v: local slabs; only the owned range is read or written.
- * All `world` ranks must call this for the same step; the call is asynchronous on `stream`. */
+ * All `world` ranks must call this for the same step; the call is asynchronous on `stream`.
+ * If a peer never reaches the matching call (crashed rank, mismatched epoch) the kernel traps after
+ * 60 s of waiting and the failure surfaces as a CUDA error on the next runtime call. */
 GACCUM_API int gaccum_apply_dp(gaccum_plan* plan, const gaccum_dp_comm* comm, float* m, float* v,
                                const gaccum_step_args* args, uint32_t epoch, gaccum_stream_t stream);
 
