@@ -159,3 +159,28 @@ def test_oracle_is_not_imported_by_the_product():
                 if f.endswith((".py", ".cu", ".cuh", ".h", ".cc")):
                     txt = open(os.path.join(dp, f), errors="ignore").read()
                     assert "import oracle" not in txt and "oracle_np" not in txt and "liboracle" not in txt, os.path.join(dp, f)
+
+
+@pytest.mark.parametrize("model", ["mnist_cnn", "bert_small", "bert_large"])
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+def test_dp_shard_ranges_partition_the_tiles_evenly(model, world):
+    """gaccum_dp_shard_range: contiguous, disjoint, covering tile ranges with near-equal element counts
+    (the fused data-parallel apply gives each rank the tiles of one range)."""
+    man = onp.MANIFESTS[model]()
+    numels = [int(np.prod(s)) for _, s in man]
+    plan = g.Plan(numels, None, g.HParams.bert(), device=-1)
+    P, nt = plan.num_elements, plan.num_tiles
+    prev_hi, total = 0, 0
+    counts = []
+    for r in range(world):
+        lo, hi, n = plan.dp_shard_range(world, r)
+        assert lo == prev_hi and hi >= lo
+        prev_hi, total = hi, total + n
+        counts.append(n)
+    assert prev_hi == nt and total == P
+    if nt >= 8 * world:
+        assert max(counts) - min(counts) <= 2 * 2048 + max(numels) % 2048 + 2048     # within a couple of tiles
+    with pytest.raises(g.GaccumError):
+        plan.dp_shard_range(9, 0)
+    with pytest.raises(g.GaccumError):
+        plan.dp_shard_range(4, 4)
