@@ -5,18 +5,20 @@
 // apply (04:59-66).  Here every rank accumulates locally for the whole window and the exchange
 // happens once, inside the apply kernel, tile by tile:
 //
-//   barrier 0  (system scope flags in symmetric memory): every rank's accumulator is final
+//   flags 0    (system-scope release/acquire words in symmetric memory, one block signals, every block
+//              waits): every rank's accumulator is final
 //   pass 1     rank r owns the tiles [tile_lo, tile_hi).  For each owned tile it LOADS THE TILE
 //              FROM EVERY RANK'S ACCUMULATOR over NVLink (peer pointers, fixed rank order
 //              0..W-1 => deterministic sum), writes the reduced a' into its own slab and
 //              reduces sum((a'/N)^2)                                  == reduce-scatter + norm
-//   barrier 1  per-rank partial norms are exchanged through the control blocks; every rank
+//   flags 1    per-rank partial norms are exchanged through the control blocks; every rank
 //              adds the W partials in rank order => bit-identical gn and clip scale everywhere
 //   pass 2     clip + AdamWeightDecay/Adam on the owned tiles (m, v are only ever touched by
 //              their owner: ZeRO-1 style), and the new parameters are STORED INTO EVERY RANK'S
 //              PARAMETER SLAB over NVLink                               == all-gather
 //              meanwhile all non-owned tiles of the local accumulator are zeroed (:86-87)
-//   barrier 2  all peers' parameter stores have landed before this kernel completes
+//   flags 2    all peers' parameter stores have landed before this kernel completes
+//   (a flag wait longer than 60 s means a dead peer: the kernel traps instead of hanging the GPU)
 //
 // NVLink bytes per rank and direction: 2 * (W-1)/W * 4P (the all-reduce lower bound); HBM
 // bytes of the update shrink to 1/W.  Parameters must live in one packed, peer-mapped slab
@@ -62,10 +64,11 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// Peer accumulator data is read exactly once per kernel, after barrier 0 (acquire at system
-// scope in block 0, then a grid-wide barrier) and L1 is invalidated at every launch, peer lines
-// bypass the local L2: a plain LDG.128 is coherent here and lets the compiler keep all W x
-// kUnroll loads in flight (NVLink latency is ~2 us; ordering them would serialise it).
+// Peer accumulator data is read exactly once per kernel, after flag round 0 (every block polls its
+// own rank's control block and issues one acquire fence at system scope), L1 is invalidated at every
+// launch and peer lines bypass the local L2: a plain LDG.128 is coherent here and lets the compiler
+// keep all W x kUnroll x tiles-per-iteration loads in flight (NVLink latency is ~2 us; ordering them
+// would serialise it).
 __device__ __forceinline__ float4 ld_peer(const float4* p) { return *p; }
 __device__ __forceinline__ float ld_peer(const float* p) { return *p; }
 
