@@ -38,7 +38,34 @@ WORKLOADS = {
     "bert_large": ("bert_large", 32, "BERT-Large L24_H1024_A16 seq512 micro_bs4 accum x32"),
 }
 INIT_LR, TRAIN_STEPS, WARMUP_STEPS = 2e-5, 207900, 20790      # reference README.md:72,75
-START_STEP = 100003      # steady state, mid-schedule; 100004 % {4,8,32} == 4 % N: the first apply comes early for N=4
+START_STEP = 100000      # steady state, mid-schedule (the per-set phases are added in run_b200_arm)
+# ONE metric string for both arms: the driver divides the two lines only when they name the same metric
+METRIC = "micro-steps/sec (train_op: accumulate + clip_by_global_norm + AdamWeightDecay apply, one window of N = N-1 accumulate + 1 apply)"
+PARITY_TOL = 1e-5        # BASELINE.json north_star: "within 1e-5 rel fp32"
+
+
+def rotation_for(accum_n: int) -> int:
+    """Number of rotating state sets: the smallest R >= 3 coprime with N, so that stepping the sets
+    round-robin can put exactly one apply launch in every N consecutive bench steps."""
+    import math
+    r = 3
+    while math.gcd(r, accum_n) != 1:
+        r += 1
+    return r
+
+
+def set_phase(r: int, R: int, N: int) -> int:
+    """global_step offset (mod N) of rotating set r such that, with set (i % R) used at bench step i, the
+    apply branch (optimization.py:91: pre-increment step % N == 0) fires exactly at i % N == N-1."""
+    if N == 1:
+        return 0
+    r_inv = pow(R, -1, N)
+    j_r = ((-1 - r) * r_inv) % N          # the uses j of set r (bench step r + R*j) that must apply
+    return (-j_r) % N
+
+
+def set_start_step(r: int, R: int, N: int) -> int:
+    return START_STEP - START_STEP % N + set_phase(r, R, N)
 
 
 def _finite(x):
@@ -57,15 +84,31 @@ def manifest(name):
     return MANIFESTS[WORKLOADS[name][0]]()
 
 
-def measured_traffic(workload):
-    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel from the committed ncu
-    capture (profiles/traffic.json); only valid for the workload it was captured on."""
+def kernel_source_stamp():
+    """sha256 over the kernel sources and build flags: ties an ncu traffic capture to the code it measured."""
+    import hashlib
+    from gaccum_b200 import build as b
+    h = hashlib.sha256()
+    for name in sorted(b.DEPS):
+        with open(os.path.join(b.CSRC, name), "rb") as f:
+            h.update(name.encode() + b"\0" + f.read())
+    h.update(" ".join(b.NVCC_FLAGS).encode())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(workload, kernel):
+    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the ncu capture
+    tools/measure_traffic.py wrote into profiles/traffic.json.  Returned only when the capture was taken
+    on this workload, this kernel and THESE kernel sources (stamp); otherwise null, never a stale number."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f)
-        return int(t["dram_bytes"]) if workload == "bert_small" else None
+        e = t["captures"][workload]
+        if e["stamp"] != kernel_source_stamp() or e["kernel"] not in kernel:
+            return None, f"profiles/traffic.json capture is for other sources/kernel (stamp {e['stamp']})"
+        return int(e["dram_bytes"]), f"profiles/traffic.json: ncu dram__bytes_read.sum+dram__bytes_write.sum per launch, stamp {e['stamp']}"
     except Exception:
-        return None
+        return None, "no capture for this workload in profiles/traffic.json"
 
 
 def peaks():
@@ -193,7 +236,7 @@ def run_reference_arm(args):
     rate, info, med = cpu_reference(wl, N, budget_s=budget, variant_b=(wl == "mnist_cnn"))
     import oracle_np
     man = oracle_np.MANIFESTS[WORKLOADS[wl][0]]()
-    out = {"impl": "reference", "metric": "micro-steps/sec (train_op only, CPU reference path)", "value": rate,
+    out = {"impl": "reference", "metric": METRIC, "value": rate,
            "unit": "micro-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": 1e3 / rate, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
@@ -231,7 +274,7 @@ def run_b200_arm(args):
     man = manifest(wl)
     names = [n for n, _ in man]
     K, W = args.steps, max(args.warmup, 3)
-    R = 3                                           # rotating state sets: defeats the 126 MB L2
+    R = rotation_for(N)                             # rotating state sets: defeats the 126 MB L2
     gen = torch.Generator(device=dev); gen.manual_seed(19830610 + 1000 * rank)
 
     def lr_fn(s):
@@ -241,19 +284,35 @@ def run_b200_arm(args):
     hp = g.HParams.tf_adam() if variant_b else g.HParams.bert()
     if args.no_clip:
         hp.clip_norm = 0.0
+
+    # ---- parity self-check (driver-visible): 2N+1 micro-steps from global_step 0 against the CPU oracle
+    #      fed the rank-summed gradients; replicas must be bit-identical.  rc != 0 above 1e-5. ----
+    parity = None
+    if args.parity_steps != 0:
+        parity = parity_check(args, wl, N, hp, variant_b, man, names, world, rank, dev, dist)
+        if parity is not None and not parity["ok"]:
+            if rank == 0:
+                print(json.dumps(_finite({"impl": "b200", "metric": METRIC, "parity": parity,
+                                          "error": "parity self-check failed; nothing was timed"})))
+            if dist is not None:
+                dist.destroy_process_group()
+            raise SystemExit(3)
+
     sets = []
     pgen = torch.Generator(device=dev); pgen.manual_seed(7)        # identical replicas on every rank
     for r in range(R):
         params = [torch.randn(s, device=dev, generator=pgen) * 0.02 for _, s in man]
         dp = None
+        # steady state, mid-schedule.  Set (i % R) serves bench step i; its global_step phase is chosen so
+        # that the apply branch fires exactly at i % N == N-1: every N consecutive bench steps are one
+        # window's launches (N-1 accumulate + 1 apply) while consecutive launches never share a state set.
+        gs0 = set_start_step(r, R, N)
         if world > 1 and args.dp == "fused":
             from gaccum_b200.distributed import FusedDataParallelTrainOp
-            dp = FusedDataParallelTrainOp(params, names, hp, N, lr_fn, global_step=START_STEP + r)
+            dp = FusedDataParallelTrainOp(params, names, hp, N, lr_fn, global_step=gs0)
             op = dp.engine
         else:
-            # steady state, mid-schedule; the sets are staggered by one micro-step so that any run of
-            # consecutive timed steps contains accumulate and apply launches in the 1 : N-1 proportion
-            op = GaccumTrainOp(params, names, hp, N, lr_fn, global_step=START_STEP + r)
+            op = GaccumTrainOp(params, names, hp, N, lr_fn, global_step=gs0)
         op.m.normal_(0, 1e-4, generator=gen); op.v.uniform_(0, 1e-8, generator=gen)
         grads = [[torch.randn(s, device=dev, generator=gen) * args.sigma for _, s in man] for _ in range(NG)]
         bound = [op.bind(gl) for gl in grads]      # what a graph-mode caller hands the op: raw pointers
@@ -280,7 +339,10 @@ def run_b200_arm(args):
             return True
         return op.run(gl)
 
-    for i in range(W * R):
+    # warm-up: at least W micro-steps per state set, rounded up to whole windows so that the timed region
+    # starts on a window boundary (bench step index % N == 0)
+    WU = -(-(W * R) // N) * N
+    for i in range(WU):
         micro_step(i)
     torch.cuda.synchronize(dev)
     if dist is not None:
@@ -290,7 +352,7 @@ def run_b200_arm(args):
     kinds = []
     sampler.start()
     torch.cuda.synchronize(dev)
-    base = W * R
+    base = WU
     torch.cuda.profiler.start()      # ncu --profile-from-start off captures only the timed region
     evs[0].record(stream)
     for i in range(K):
@@ -370,36 +432,53 @@ def run_b200_arm(args):
             dist.destroy_process_group()
         return
     peak, peak_src = peaks()
+    # own kernels launched per rank inside the timed region: one per micro-step, plus whatever extra the
+    # data-parallel apply step needs (fused: none; nccl all-reduce baseline: accumulate + apply = 2)
+    per_apply = getattr(sets[0][4], "launches_per_apply", 2) if world > 1 else 1
+    launches_per_rank = K + len(apply_ms) * (per_apply - 1)
     ab = sets[0][0].plan.algorithmic_bytes(True)
     acb = sets[0][0].plan.algorithmic_bytes(False)
     a_ms, c_ms = mean(apply_ms), mean(acc_ms)
     achieved = ab / (a_ms * 1e-3) / 1e9 if apply_ms else float("nan")
+    if world == 1:
+        kernel = ("apply_clip_kernel (a+=G, /N, global-norm clip, AdamWeightDecay, a=0; one cooperative launch, TMA-fed pass 1)"
+                  if hp.clip_norm > 0 else "apply_kernel (single pass: a+=G, /N, Adam, a=0; no clip)")
+    else:
+        kernel = "dp_apply_kernel (apply step at N>1: includes the NVLink exchange, so this is not an HBM roofline)"
+    traffic, traffic_src = measured_traffic(wl, kernel) if world == 1 else (None, "not captured at N>1")
+    window_exact = len(apply_ms) * (N - 1) == len(acc_ms)
+    # window-exact rate from the per-kind means (what any whole number of windows costs), beside `value`
+    window_us = ((N - 1) * c_ms + a_ms) * 1e3 if (apply_ms and (acc_ms or N == 1)) else None
     out = {
-        "metric": "micro-steps/sec (train_op only: accumulate + clip + AdamWeightDecay apply)",
-        "value": world * K / (total_ms * 1e-3), "unit": "micro-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+        "impl": "b200",
+        "metric": METRIC,
+        "value": world * K / (total_ms * 1e-3), "unit": "micro-steps/s", "n_gpus": world, "steps": K, "warmup": WU,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{wl}_accum{N}", "desc": WORKLOADS[wl][2], "T": len(man), "P": P, "accum_n": N,
                    "optimizer": "tf.train.AdamOptimizer" if variant_b else "AdamWeightDecay+clip_by_global_norm(1.0)",
                    "grad_sigma": args.sigma,
                    "parallelism": f"dp{world}" + ("" if world == 1 else
-                                                   " fused apply kernel: reduce-scatter by NVLink peer loads + sharded update + all-gather by peer stores"
+                                                   " fused apply kernel: local a+=G + reduce-scatter + sharded update + all-gather over NVLink peer memory in one launch"
                                                    if args.dp == "fused" else " nccl all-reduce of the packed accum slab on apply steps"),
                    "l2": f"rotating {R} independent state sets ({R * 5 * 4 * P / 1e6:.0f} MB of state+grads per rotation) > 126 MB L2",
-                   "apply_launches": len(apply_ms), "accumulate_launches": len(acc_ms)},
-        "roofline": {"bound": "hbm", "kernel": (("apply_clip2_kernel (a+=G, /N, global-norm clip, AdamWeightDecay, a=0; one cooperative launch)"
-                                           if hp.clip_norm > 0 else "apply_kernel (single pass: a+=G, /N, Adam, a=0; no clip)") if world == 1 else
-                                          "accumulate_kernel + dp_apply_kernel (apply step at N>1: includes the NVLink exchange, so this is not an HBM roofline)"),
+                   "apply_launches": len(apply_ms), "accumulate_launches": len(acc_ms),
+                   "window_exact": window_exact,
+                   "window_exact_value": (world * N / (window_us * 1e-6)) if window_us else None,
+                   "mix_note": "bench step i uses state set i % R and applies iff i % N == N-1 (phased global_steps); "
+                               "the timed region starts on a window boundary, so K % N == 0 gives exactly K/N windows"},
+        "roofline": {"bound": "hbm", "kernel": kernel,
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "algorithmic_bytes": ab, "avg_launch_us": a_ms * 1e3,
-                     "traffic": measured_traffic(wl) if (world == 1 and not args.no_clip) else None,
-                     "traffic_source": "profiles/traffic.json (ncu --set full, dram__bytes_read+write per launch)"},
+                     "traffic": traffic, "traffic_source": traffic_src},
         "roofline_accumulate": {"bound": "hbm", "kernel": "accumulate_kernel", "achieved": acb / (c_ms * 1e-3) / 1e9 if acc_ms else None,
                                 "peak": peak, "unit": "GB/s", "frac": (acb / (c_ms * 1e-3) / 1e9 / peak) if acc_ms else None,
                                 "algorithmic_bytes": acb, "avg_launch_us": c_ms * 1e3 if acc_ms else None},
-        "gpu_launches": K + (len(apply_ms) if world > 1 else 0),   # DP apply steps = local accumulate + fused exchange/apply kernel
+        "gpu_launches": launches_per_rank,
         "clocks": clocks,
     }
+    if parity is not None:
+        out["parity"] = parity
     if e2e:
         out["e2e"] = e2e
     if with_model:
@@ -421,6 +500,118 @@ def run_b200_arm(args):
     print(json.dumps(_finite(out)))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def parity_check(args, wl, N, hp, variant_b, man, names, world, rank, dev, dist):
+    """Driver-visible parity of the path that is about to be timed (reference semantics:
+    optimization.py:76-104 on one GPU; 04_multi_worker_with_estimator_gaccum.py:46,55,58,62 on W GPUs).
+
+    Every rank runs `steps` micro-steps from global_step 0 (so the windows are {0}, {1..N}, {N+1..2N}) on
+    the workload's real shapes with gradients from numpy PCG64(19830610 + 1000*rank + step), pre-divided by
+    the number of workers as 04:46 does.  Rank 0 feeds the CPU oracle (checker use of oracle/) the
+    rank-ordered fp32 sum of all ranks' gradients and compares parameters, adam_m, adam_v after the last
+    step; replicas are compared bit for bit through int32 min/max all-reduces of the parameter slab."""
+    import numpy as np
+    import torch
+    import gaccum_b200 as g
+    from gaccum_b200.train_op import GaccumTrainOp
+    Np = min(N, 4)                                   # parity window (keeps BERT-Large x N=32 affordable)
+    steps = args.parity_steps if args.parity_steps > 0 else 2 * Np + 1
+    sigma = args.sigma
+    if variant_b:
+        lr_kw, lr_fn = dict(constant_lr=1e-4), (lambda s: 1e-4)
+    else:
+        # a short schedule so that lr is O(init_lr) from the first apply on (warm-up of 2 micro-steps)
+        sched = dict(init_lr=INIT_LR, num_train_steps=1000, num_warmup_steps=2)
+        lr_kw, lr_fn = sched, (lambda s: g.learning_rate(sched["init_lr"], sched["num_train_steps"], sched["num_warmup_steps"], s))
+    prng = np.random.Generator(np.random.PCG64(19830610))
+    host_params = [prng.standard_normal(s, dtype=np.float32) * np.float32(0.02) for _, s in man]
+    params = [torch.from_numpy(p).to(dev) for p in host_params]
+    dp = None
+    if world > 1 and args.dp == "fused":
+        from gaccum_b200.distributed import FusedDataParallelTrainOp
+        dp = FusedDataParallelTrainOp(params, names, hp, Np, lr_fn)
+        op, runner = dp.engine, dp
+    elif world > 1:
+        from gaccum_b200.distributed import DataParallelTrainOp
+        op = GaccumTrainOp(params, names, hp, Np, lr_fn)
+        runner = DataParallelTrainOp(op, None)
+    else:
+        op = runner = GaccumTrainOp(params, names, hp, Np, lr_fn)
+    ref = None
+    if rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle_c
+        import oracle_np as onp
+        ohp = onp.HParams.tf_adam() if variant_b else onp.HParams.bert()
+        ohp.clip_norm = float(hp.clip_norm)
+        ref = oracle_c.COracleTrainOp([p.copy() for p in host_params], names, ohp, Np, **lr_kw)
+    sizes = [int(np.prod(s)) for _, s in man]
+    Ptot = sum(sizes)
+    flat = torch.empty(Ptot, dtype=torch.float32, device=dev)
+    gathered = [torch.empty_like(flat) for _ in range(world)] if (world > 1 and rank == 0) else None
+    t0 = time.perf_counter()
+    for step in range(steps):
+        rng = np.random.Generator(np.random.PCG64(19830610 + 1000 * rank + step))
+        hg = rng.standard_normal(Ptot, dtype=np.float32) * np.float32(sigma / world)    # 04:46 loss / num_workers
+        flat.copy_(torch.from_numpy(hg))
+        grads, o = [], 0
+        for (_, shp), n in zip(man, sizes):
+            grads.append(flat[o:o + n].view(shp)); o += n
+        runner.run(grads)
+        if world > 1:
+            dist.gather(flat, gathered, dst=0)
+        if rank == 0:
+            if world > 1:
+                tot = gathered[0].clone()
+                for w in range(1, world):
+                    tot += gathered[w]                       # fp32, rank order
+                hsum = tot.cpu().numpy()
+            else:
+                hsum = hg
+            og, o = [], 0
+            for (_, shp), n in zip(man, sizes):
+                og.append(hsum[o:o + n].reshape(shp)); o += n
+            ref.run(og)
+    torch.cuda.synchronize(dev)
+    st = op.stats()
+    # replicas: bitwise identity of the parameters on every rank
+    identical = True
+    if world > 1:
+        pslab = dp.param_slab if dp is not None else torch.cat([p.reshape(-1) for p in params])
+        lo = pslab.view(torch.int32).clone(); hi = lo.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        identical = bool(torch.equal(lo, hi))
+    full = dp.gather_state() if dp is not None else {"m": op.m, "v": op.v}
+    out = None
+    if rank == 0:
+        worst, worst_at = 0.0, None
+        offs = op.plan.offsets
+        hm, hv = full["m"].cpu().numpy(), full["v"].cpu().numpy()
+        for i, (nm, shp) in enumerate(man):
+            n = sizes[i]
+            for kind, got, exp in (("param", params[i].cpu().numpy(), ref.params[i]),
+                                   ("adam_m", hm[offs[i]:offs[i] + n].reshape(shp), ref.m[i]),
+                                   ("adam_v", hv[offs[i]:offs[i] + n].reshape(shp), ref.v[i])):
+                denom = max(float(np.max(np.abs(exp))) if n else 0.0, 1e-30)
+                e = float(np.max(np.abs(got.astype(np.float64) - exp.astype(np.float64)))) / denom if n else 0.0
+                if not (e <= worst):                        # NaN-safe: a NaN error becomes the worst
+                    worst, worst_at = e, f"{kind}:{nm}"
+        ok = bool(worst <= PARITY_TOL) and identical
+        out = {"max_rel_err": worst, "worst": worst_at, "tol": PARITY_TOL, "replicas_identical": identical, "world": world,
+               "steps": steps, "accum_n": Np, "applies": sum(1 for s_ in range(steps) if s_ % Np == 0),
+               "last_clip_scale": st["clip_scale"], "last_global_norm": st["global_norm"],
+               "oracle": "oracle/oracle.c (CPU restatement of optimization.py) fed the fp32 rank-ordered sum of all ranks' gradients",
+               "grads": "numpy PCG64(19830610 + 1000*rank + step), N(0, sigma^2)/world", "wall_s": time.perf_counter() - t0,
+               "ok": ok}
+    if world > 1:
+        flag = torch.tensor([1 if (out is None or out["ok"]) else 0], device=dev)
+        dist.broadcast(flag, src=0)
+        if out is None:
+            out = {"ok": bool(flag.item())}
+    del runner, op, dp, params
+    torch.cuda.empty_cache()
+    return out
 
 
 def with_model_leg(args, wl, N, hp, lr_fn, world, rank, dev, dist):
@@ -496,6 +687,7 @@ def main():
     ap.add_argument("--no-clip", action="store_true", help="experiment: AdamWeightDecay without clip_by_global_norm (single-pass apply)")
     ap.add_argument("--model-steps", type=int, default=48, help="micro-steps of the with-model leg (0 disables)")
     ap.add_argument("--e2e-steps", type=int, default=48)
+    ap.add_argument("--parity-steps", type=int, default=-1, help="micro-steps of the pre-timing parity self-check against the CPU oracle (-1: 2*min(N,4)+1, 0: skip)")
     ap.add_argument("--e2e-keep-affinity", action="store_true", help="experiment: keep the GPU-local CPU affinity for the whole e2e leg")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-oracle timing (0 disables)")
     args = ap.parse_args()

@@ -9,7 +9,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libgaccum.so")
 SOURCES = ["gaccum_abi.cu"]
-DEPS = SOURCES + ["gaccum_kernels.cuh", "../../include/gaccum.h"]
+# every file the translation unit includes: editing any of them must rebuild libgaccum.so (a stale binary
+# travels to the GPU box and silently runs old kernels)
+DEPS = SOURCES + sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + ["../../include/gaccum.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",

@@ -13,6 +13,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """gpu-marked tests need a CUDA device: on a box without one they are skipped, not failed
+    (the product itself still fails loudly there -- tests/test_host_logic.py checks that)."""
+    try:
+        import torch
+        have = torch.cuda.is_available()
+    except Exception:
+        have = False
+    if have:
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
 @pytest.fixture(scope="session", autouse=True)
 def _built():
     """Both shared objects exist before any test runs (nvcc cross-compiles without a GPU)."""
