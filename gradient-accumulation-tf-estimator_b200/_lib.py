@@ -45,9 +45,10 @@ DP_CTRL_BYTES = 256
 
 
 class DpComm(C.Structure):
-    """gaccum_dp_comm: peer base pointers for the fused data-parallel apply."""
-    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("accum_peers", C.c_void_p * MAX_RANKS),
-                ("param_peers", C.c_void_p * MAX_RANKS), ("ctrl_peers", C.c_void_p * MAX_RANKS)]
+    """gaccum_dp_comm: the local accumulator slab + peer base pointers for the fused data-parallel apply."""
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("accum", C.c_void_p),
+                ("param_peers", C.c_void_p * MAX_RANKS), ("stage_peers", C.c_void_p * MAX_RANKS),
+                ("ctrl_peers", C.c_void_p * MAX_RANKS), ("stage_elements", C.c_int64)]
 
 
 class Stats(C.Structure):
@@ -67,8 +68,13 @@ def _load():
     global _lib
     if _lib is not None:
         return _lib
+    override = os.environ.get("GACCUM_LIB")    # measurement builds (build.build_variant), never a fallback
+    if override:
+        if not os.path.exists(override):
+            raise ImportError(f"GACCUM_LIB={override} does not exist")
+        _build.LIB = override
     try:
-        path = _build.build_libgaccum()
+        path = override or _build.build_libgaccum()
     except Exception as e:  # no nvcc and no prebuilt library: fail loudly, never fall back
         if not os.path.exists(_build.LIB):
             raise ImportError(f"libgaccum.so is missing and cannot be built ({e}); "
@@ -103,7 +109,9 @@ def _load():
         "gaccum_host_session_sync": (C.c_int, [vp]),
         "gaccum_host_session_slabs": (C.c_int, [vp, vp]),
         "gaccum_dp_shard_range": (C.c_int, [vp, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]),
-        "gaccum_apply_dp": (C.c_int, [vp, C.POINTER(DpComm), vp, vp, C.POINTER(StepArgs), C.c_uint32, vp]),
+        "gaccum_dp_stage_elements": (i64, [vp, i32]),
+        "gaccum_apply_dp": (C.c_int, [vp, C.POINTER(DpComm), vp, vp, vp, C.POINTER(StepArgs), C.c_uint32, vp]),
+        "gaccum_step_dp": (C.c_int, [vp, C.POINTER(DpComm), vp, vp, vp, C.POINTER(StepArgs), C.c_uint32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -201,8 +209,17 @@ class Plan:
         _check(_load().gaccum_dp_shard_range(self._h, world, rank, C.byref(lo), C.byref(hi), C.byref(n)))
         return lo.value, hi.value, n.value
 
-    def apply_dp(self, comm: "DpComm", m: int, v: int, args: StepArgs, epoch: int, stream: int = 0) -> None:
-        _check(_load().gaccum_apply_dp(self._h, C.byref(comm), m, v, C.byref(args), epoch, stream))
+    def dp_stage_elements(self, world: int) -> int:
+        n = int(_load().gaccum_dp_stage_elements(self._h, world))
+        if n < 0:
+            _check(n)
+        return n
+
+    def apply_dp(self, comm: "DpComm", grads, m: int, v: int, args: StepArgs, epoch: int, stream: int = 0) -> None:
+        _check(_load().gaccum_apply_dp(self._h, C.byref(comm), grads, m, v, C.byref(args), epoch, stream))
+
+    def step_dp(self, comm: "DpComm", grads, m: int, v: int, args: StepArgs, epoch: int, stream: int = 0) -> None:
+        _check(_load().gaccum_step_dp(self._h, C.byref(comm), grads, m, v, C.byref(args), epoch, stream))
 
     def read_stats(self, host_ptr: int, stream: int = 0) -> None:
         _check(_load().gaccum_read_stats(self._h, host_ptr, stream))

@@ -59,17 +59,17 @@ struct gaccum_plan {
   // device side
   TileDesc* d_tiles = nullptr;
   double* d_partials = nullptr;
-  float* d_tile_sumsq = nullptr;
-  uint32_t* d_tickets = nullptr;
   float* d_stats = nullptr;
-  float* d_bcast = nullptr;
-  unsigned long long* d_debug = nullptr;   // GACCUM_EXPERIMENTS only
+  uint32_t* d_dp_sync = nullptr;           // data-parallel kernel: block-completion counters (zero between launches)
+#ifdef GACCUM_EXPERIMENTS
+  unsigned long long* d_debug = nullptr;   // per-CTA timestamps (tools/cta_timeline.py; experiments build only)
+#endif
   int num_sms = 0;
   int max_grid = 0;
-  uint32_t tune = 0;   // kTune* bits; GACCUM_TUNE overrides (experiments)
+  uint32_t flags = 0;  // kFlag* bits; GACCUM_FLAGS selects A/B measurement variants (all compute the same result)
   std::mutex mu;
   std::map<const void*, int> grid_cache;   // kernel -> co-resident grid size
-  std::map<const void*, int> stash_cache;  // kernel -> shared-memory stash tiles per CTA
+  std::map<const void*, int> stash_cache;  // kernel -> shared-memory stash tiles per consumer group
   int smem_per_sm = 0, smem_optin = 0, stash_override = -1;
 };
 
@@ -154,105 +154,72 @@ static int grid_for(gaccum_plan* pl, const void* fn, int* out) {
 
 template <int CAP>
 static int launch_accumulate(gaccum_plan* pl, KernelParams<CAP>& prm, cudaStream_t st) {
-  const void* fn = (const void*)&accumulate_kernel<CAP>;
-  int grid = 0;
-  if (int rc = grid_for(pl, fn, &grid)) return rc;
-  grid = std::max(1, std::min(grid, prm.num_tiles));
-  if (pl->tune & kTuneAccTiles) grid = std::max(1, prm.num_tiles);
+  // one tile per CTA: the hardware block scheduler balances better than a persistent loop (r01_tune_sweep.md)
+  const int grid = std::max(1, prm.num_tiles);
   accumulate_kernel<CAP><<<grid, kThreads, 0, st>>>(prm);
   CUDA_TRY(cudaGetLastError());
   return GACCUM_OK;
 }
 
-template <int VARIANT, bool CLIP, bool HAS_G, int CAP>
-static int launch_apply_inst(gaccum_plan* pl, KernelParams<CAP>& prm, cudaStream_t st) {
-  const void* fn = (const void*)&apply_kernel<VARIANT, CLIP, HAS_G, CAP>;
-  int grid = 0;
-  if (int rc = grid_for(pl, fn, &grid)) return rc;
-  grid = std::max(1, std::min(grid, prm.num_tiles));
-  if (CLIP) {
-    void* args[] = {(void*)&prm};
-    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, 0, st));
-  } else {
-    if (pl->tune & kTuneAccTiles) grid = std::max(1, prm.num_tiles);
-    apply_kernel<VARIANT, CLIP, HAS_G, CAP><<<grid, kThreads, 0, st>>>(prm);
-    CUDA_TRY(cudaGetLastError());
-  }
+template <int VARIANT, bool HAS_G, int CAP>
+static int launch_apply_noclip(gaccum_plan* pl, KernelParams<CAP>& prm, cudaStream_t st) {
+  const int grid = std::max(1, prm.num_tiles);
+  apply_kernel<VARIANT, HAS_G, CAP><<<grid, kThreads, 0, st>>>(prm);
+  CUDA_TRY(cudaGetLastError());
   return GACCUM_OK;
 }
 
-// v2: static two-pass + shared-memory stash (+ optional ordinary launch with an atomic barrier)
-template <int VARIANT, bool HAS_G, int CAP, bool USE_TMEM>
-static int launch_apply_clip2_t(gaccum_plan* pl, KernelParams<CAP>& prm, cudaStream_t st) {
-  const void* fn = (const void*)&apply_clip2_kernel<VARIANT, HAS_G, CAP, USE_TMEM>;
-  int grid = 0, stash = 0;
+// clip-apply: one cooperative launch, ONE 864-thread CTA per SM (it allocates all of Tensor Memory and most of
+// shared memory, so a second CTA could never be co-resident -- the grid is clamped to the SM count, not
+// derived from the occupancy API)
+template <int VARIANT, bool HAS_G, int CAP>
+static int launch_apply_clip(gaccum_plan* pl, KernelParams<CAP>& prm, cudaStream_t st) {
+  const void* fn = (const void*)&apply_clip_kernel<VARIANT, HAS_G, CAP>;
+  int slots = 0;
   {
     std::lock_guard<std::mutex> lk(pl->mu);
-    auto it = pl->grid_cache.find(fn);
-    if (it == pl->grid_cache.end()) {
-      // keep the register-limited occupancy and give every resident CTA an equal share of shared memory
-      constexpr int kGroups = USE_TMEM ? kGroups3 : 1;
-      constexpr int kBlock = kThreads * kGroups;
+    auto it = pl->stash_cache.find(fn);
+    if (it == pl->stash_cache.end()) {
+      cudaFuncAttributes fa{};
+      CUDA_TRY(cudaFuncGetAttributes(&fa, fn));
+      const int group_bytes = kSlotVecs * 16 * kGroups;          // one slot for each of the three groups
+      // kMaxSlots x 3 x 8 KB = 192 KB is the largest pool that fits the 196 KB shared-memory carve-out: one step
+      // more and L1 drops from 60 KB to 28 KB, which starves pass 2's in-flight loads (measured, r02_tune_sweep.md)
+      int s_tiles = std::min(kMaxSlots, (pl->smem_optin - (int)fa.sharedSizeBytes) / group_bytes);
+      if (pl->stash_override > 0) s_tiles = std::min(s_tiles, pl->stash_override);
+      if (s_tiles < 1) return fail(GACCUM_ECUDA, "apply_clip_kernel: no room for one tile slot per group in shared memory");
+      const int dyn = s_tiles * group_bytes;
+      CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
       int per_sm = 0;
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlock, 0));
-      if (per_sm < 1) return fail(GACCUM_ECUDA, "kernel does not fit on an SM");
-      const int tile_bytes = kTile * (int)sizeof(float) * kGroups;          // every group gets its own stash
-      int s_tiles = (pl->smem_per_sm / per_sm - 1024 - 512) / tile_bytes;     // 1 KB driver reserve per CTA
-      s_tiles = std::max(0, std::min(s_tiles, (pl->smem_optin - 512) / tile_bytes));
-      // measured (profiles/r01_tune_sweep.md): 8 tiles/CTA is the sweet spot; 9 starves L1 of the
-      // lines it needs for in-flight loads and costs 15 %
-      s_tiles = std::min(s_tiles, pl->stash_override >= 0 ? pl->stash_override : 8);
-      CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(1, s_tiles) * tile_bytes));
-      int check = 0;
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&check, fn, kBlock, (size_t)s_tiles * tile_bytes));
-      if (check < per_sm) { s_tiles = 0; }                                   // never trade occupancy for stash
-      pl->grid_cache[fn] = std::min(per_sm * pl->num_sms, pl->max_grid);
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kClipThreads, (size_t)dyn));
+      if (per_sm < 1) return fail(GACCUM_ECUDA, "apply_clip_kernel does not fit on an SM (%d B dynamic shared memory)", dyn);
       pl->stash_cache[fn] = s_tiles;
-      it = pl->grid_cache.find(fn);
+      it = pl->stash_cache.find(fn);
     }
-    grid = it->second;
-    stash = pl->stash_cache[fn];
+    slots = it->second;
   }
-  constexpr int kGroupsL = USE_TMEM ? kGroups3 : 1;
-  grid = std::max(1, std::min(grid, (prm.num_tiles + kGroupsL - 1) / kGroupsL));
-  prm.stash_tiles = stash;
-  prm.tmem_tiles = USE_TMEM ? kTmemTiles : 0;
-  const size_t smem = (size_t)stash * kTile * sizeof(float) * kGroupsL;
-  if (pl->tune & kTuneOwnBarrier) {
-    apply_clip2_kernel<VARIANT, HAS_G, CAP, USE_TMEM><<<grid, kThreads * kGroupsL, smem, st>>>(prm);
-    CUDA_TRY(cudaGetLastError());
-  } else {
-    void* args[] = {(void*)&prm};
-    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads * kGroupsL), args, smem, st));
-  }
+  const int grid = std::max(1, std::min(pl->num_sms, (prm.num_tiles + kGroups - 1) / kGroups));
+  prm.stash_tiles = slots;
+  prm.tmem_tiles = kTmemTiles;
+  const size_t smem = (size_t)slots * kSlotVecs * 16 * kGroups;
+  void* args[] = {(void*)&prm};
+  CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kClipThreads), args, smem, st));
   return GACCUM_OK;
-}
-
-template <int VARIANT, bool HAS_G, int CAP>
-static int launch_apply_clip2(gaccum_plan* pl, KernelParams<CAP>& prm, cudaStream_t st) {
-  return (pl->tune & kTuneTmemStash) ? launch_apply_clip2_t<VARIANT, HAS_G, CAP, true>(pl, prm, st)
-                                     : launch_apply_clip2_t<VARIANT, HAS_G, CAP, false>(pl, prm, st);
 }
 
 template <int CAP>
 static int launch_apply(gaccum_plan* pl, KernelParams<CAP>& prm, bool has_g, cudaStream_t st) {
   const bool clip = pl->hp.clip_norm > 0.0;
-  if (clip && !(pl->tune & kTuneApplyV1)) {
-    if (pl->hp.variant == GACCUM_ADAM)
-      return has_g ? launch_apply_clip2<1, true>(pl, prm, st) : launch_apply_clip2<1, false>(pl, prm, st);
-    return has_g ? launch_apply_clip2<0, true>(pl, prm, st) : launch_apply_clip2<0, false>(pl, prm, st);
-  }
-
   const int key = (pl->hp.variant == GACCUM_ADAM ? 4 : 0) | (clip ? 2 : 0) | (has_g ? 1 : 0);
   switch (key) {
-    case 0: return launch_apply_inst<0, false, false>(pl, prm, st);
-    case 1: return launch_apply_inst<0, false, true>(pl, prm, st);
-    case 2: return launch_apply_inst<0, true, false>(pl, prm, st);
-    case 3: return launch_apply_inst<0, true, true>(pl, prm, st);
-    case 4: return launch_apply_inst<1, false, false>(pl, prm, st);
-    case 5: return launch_apply_inst<1, false, true>(pl, prm, st);
-    case 6: return launch_apply_inst<1, true, false>(pl, prm, st);
-    default: return launch_apply_inst<1, true, true>(pl, prm, st);
+    case 0: return launch_apply_noclip<0, false>(pl, prm, st);
+    case 1: return launch_apply_noclip<0, true>(pl, prm, st);
+    case 2: return launch_apply_clip<0, false>(pl, prm, st);
+    case 3: return launch_apply_clip<0, true>(pl, prm, st);
+    case 4: return launch_apply_noclip<1, false>(pl, prm, st);
+    case 5: return launch_apply_noclip<1, true>(pl, prm, st);
+    case 6: return launch_apply_clip<1, false>(pl, prm, st);
+    default: return launch_apply_clip<1, true>(pl, prm, st);
   }
 }
 
@@ -277,11 +244,11 @@ static void fill_common(gaccum_plan* pl, KernelParams<CAP>& prm, float* accum, f
   prm.m = m;
   prm.v = v;
   prm.partials = pl->d_partials;
-  prm.tile_sumsq = pl->d_tile_sumsq;
-  prm.tickets = pl->d_tickets;
+#ifdef GACCUM_EXPERIMENTS
   prm.debug = pl->d_debug;
+#endif
   prm.stats = pl->d_stats;
-  prm.tune = pl->tune;
+  prm.flags = pl->flags;
   prm.sc = sc;
 }
 
@@ -309,11 +276,11 @@ struct DeviceGuard {
 
 template <int CAP>
 static int do_accumulate_tab(gaccum_plan* pl, const float* const* grads, float* accum,
-                             const gaccum_step_args* a, cudaStream_t st, uint32_t extra_tune = 0) {
+                             const gaccum_step_args* a, cudaStream_t st, uint32_t extra_flags = 0) {
   KernelParams<CAP>* prm = new (std::nothrow) KernelParams<CAP>();
   if (!prm) return fail(GACCUM_ENOMEM, "out of host memory");
   fill_common(pl, *prm, accum, nullptr, nullptr, make_scalars(pl->hp, a));
-  prm->tune |= extra_tune;
+  prm->flags |= extra_flags;
   int rc = fill_table(pl, prm->tab, grads, nullptr);
   if (rc == GACCUM_OK) rc = launch_accumulate(pl, *prm, st);
   delete prm;
@@ -337,6 +304,13 @@ static int check_args(const gaccum_step_args* a) {
   if (a->accum_n <= 0) return fail(GACCUM_EINVAL, "accum_n must be > 0 (got %d)", a->accum_n);
   if (a->reserved != 0 || a->reserved2 != 0.0f) return fail(GACCUM_EINVAL, "reserved fields must be 0");
   return GACCUM_OK;
+}
+
+static void free_plan_device(gaccum_plan* pl) {
+  cudaFree(pl->d_tiles); cudaFree(pl->d_partials); cudaFree(pl->d_stats); cudaFree(pl->d_dp_sync);
+#ifdef GACCUM_EXPERIMENTS
+  cudaFree(pl->d_debug);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
@@ -430,15 +404,9 @@ int gaccum_plan_create(gaccum_plan** out, int32_t T, const int64_t* numels, cons
   if (hp->variant == GACCUM_ADAM_WEIGHT_DECAY && decay) pl->decay.assign(decay, decay + T);
   if (int rc = build_layout(pl)) { delete pl; return rc; }
   pl->device = -1;
-  // measured best on B200 (profiles/r01_tune_sweep.md): evict_last a', streaming state, tile-per-CTA
-  // accumulate, shared-memory + Tensor-Memory stash of a'.  GACCUM_TUNE overrides for A/B sweeps; the
-  // bits that skip work (timing decomposition, WRONG results) additionally need GACCUM_EXPERIMENTS=1.
-  pl->tune = kTuneKeepA | kTuneStreamState | kTuneAccTiles | kTuneStaticApply | kTuneTmemStash | kTunePrefetch;
-  if (const char* t = getenv("GACCUM_TUNE")) pl->tune = (uint32_t)strtoul(t, nullptr, 0);
-  if ((pl->tune & (kTuneSkipPass1 | kTuneSkipPass2 | kTuneSkipZero)) && !getenv("GACCUM_EXPERIMENTS")) {
-    delete pl;
-    return fail(GACCUM_EINVAL, "GACCUM_TUNE requests a timing experiment that produces wrong results; set GACCUM_EXPERIMENTS=1 to allow it");
-  }
+  // GACCUM_FLAGS: A/B measurement variants of the clip-apply kernel (kFlag* in gaccum_kernels.cuh); every
+  // combination computes the same result.  Timing experiments that change results do not exist in this build.
+  if (const char* t = getenv("GACCUM_FLAGS")) pl->flags = (uint32_t)strtoul(t, nullptr, 0) & (kFlagNoL2Prefetch | kFlagNoCrossPrefetch);
   if (device >= 0) {
     int n = gaccum_device_count();
     if (device >= n) { delete pl; return fail(GACCUM_ENODEVICE, "CUDA device %d requested but %d device(s) visible; libgaccum has no CPU fallback", device, n); }
@@ -456,19 +424,16 @@ int gaccum_plan_create(gaccum_plan** out, int32_t T, const int64_t* numels, cons
     if (e == cudaSuccess && !pl->tiles.empty())
       e = cudaMemcpy(pl->d_tiles, pl->tiles.data(), pl->tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_partials, sizeof(double) * (size_t)pl->max_grid);
-    if (e == cudaSuccess) e = cudaMalloc(&pl->d_tile_sumsq, sizeof(float) * std::max<size_t>(1, pl->tiles.size()));
-    if (e == cudaSuccess) e = cudaMalloc(&pl->d_tickets, sizeof(uint32_t) * 4);
-    if (e == cudaSuccess) e = cudaMemset(pl->d_tickets, 0, sizeof(uint32_t) * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&pl->d_bcast, 4 * sizeof(float));
-    if (e == cudaSuccess && getenv("GACCUM_EXPERIMENTS")) {
-      e = cudaMalloc(&pl->d_debug, sizeof(unsigned long long) * 4 * (size_t)pl->max_grid);
-      if (e == cudaSuccess) e = cudaMemset(pl->d_debug, 0, sizeof(unsigned long long) * 4 * (size_t)pl->max_grid);
-    }
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_dp_sync, sizeof(uint32_t) * 8);
+    if (e == cudaSuccess) e = cudaMemset(pl->d_dp_sync, 0, sizeof(uint32_t) * 8);
+#ifdef GACCUM_EXPERIMENTS
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_debug, sizeof(unsigned long long) * 16 * (size_t)pl->max_grid);
+    if (e == cudaSuccess) e = cudaMemset(pl->d_debug, 0, sizeof(unsigned long long) * 16 * (size_t)pl->max_grid);
+#endif
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_stats, sizeof(gaccum_stats));
     if (e == cudaSuccess) e = cudaMemset(pl->d_stats, 0, sizeof(gaccum_stats));
     if (e != cudaSuccess) {
-      cudaFree(pl->d_tiles); cudaFree(pl->d_partials); cudaFree(pl->d_stats);
-    cudaFree(pl->d_tile_sumsq); cudaFree(pl->d_tickets); cudaFree(pl->d_bcast); cudaFree(pl->d_debug);
+      free_plan_device(pl);
       delete pl;
       return fail(GACCUM_ECUDA, "plan device setup failed: %s", cudaGetErrorString(e));
     }
@@ -482,8 +447,7 @@ int gaccum_plan_destroy(gaccum_plan* pl) {
   if (!pl) return GACCUM_OK;
   if (pl->device >= 0) {
     DeviceGuard guard(pl->device);
-    cudaFree(pl->d_tiles); cudaFree(pl->d_partials); cudaFree(pl->d_stats);
-    cudaFree(pl->d_tile_sumsq); cudaFree(pl->d_tickets); cudaFree(pl->d_bcast); cudaFree(pl->d_debug);
+    free_plan_device(pl);
   }
   delete pl;
   return GACCUM_OK;
@@ -560,11 +524,10 @@ int gaccum_step_packed(gaccum_plan* pl, const float* grad_slab, float* param_sla
   return launch_apply(pl, prm, grad_slab != nullptr, st);
 }
 
-static void shard_range(const gaccum_plan* pl, int world, int rank, int* lo, int* hi, int64_t* elems) {
-  // contiguous tile ranges with (nearly) equal element counts: boundary r = first tile whose
-  // cumulative element count reaches r * P / world
+// contiguous tile ranges with (nearly) equal element counts: boundary r = first tile whose cumulative
+// element count reaches r * P / world
+static void shard_bounds(const gaccum_plan* pl, int world, int* bounds /* world + 1 */) {
   const int nt = (int)pl->tiles.size();
-  int bounds[GACCUM_MAX_RANKS + 1];
   int64_t cum = 0;
   int r = 1;
   bounds[0] = 0;
@@ -573,11 +536,19 @@ static void shard_range(const gaccum_plan* pl, int world, int rank, int* lo, int
     while (r < world && cum >= (pl->P * r + world - 1) / world) bounds[r++] = t + 1;
   }
   while (r <= world) bounds[r++] = nt;
-  *lo = bounds[rank];
-  *hi = bounds[rank + 1];
-  int64_t e = 0;
-  for (int t = *lo; t < *hi; ++t) e += pl->tiles[t].len;
-  if (elems) *elems = e;
+}
+// slab offset (in units of 32 elements) at which tile t starts; t == num_tiles -> end of the slab
+static uint32_t tile_soff32(const gaccum_plan* pl, int t) {
+  return t < (int)pl->tiles.size() ? pl->tiles[t].soff32 : (uint32_t)(pl->padded / kSlabAlign);
+}
+// elements of one source region of a staging area = the widest shard's slab span
+static int64_t stage_span(const gaccum_plan* pl, int world) {
+  int bounds[GACCUM_MAX_RANKS + 1];
+  shard_bounds(pl, world, bounds);
+  int64_t span = 0;
+  for (int r = 0; r < world; ++r)
+    span = std::max<int64_t>(span, ((int64_t)tile_soff32(pl, bounds[r + 1]) - (int64_t)tile_soff32(pl, bounds[r])) * kSlabAlign);
+  return std::max<int64_t>(span, kSlabAlign);
 }
 
 int gaccum_dp_shard_range(const gaccum_plan* pl, int32_t world, int32_t rank, int32_t* tile_lo,
@@ -585,55 +556,96 @@ int gaccum_dp_shard_range(const gaccum_plan* pl, int32_t world, int32_t rank, in
   if (!pl || !tile_lo || !tile_hi) return fail(GACCUM_EINVAL, "bad arguments to gaccum_dp_shard_range");
   if (world < 1 || world > GACCUM_MAX_RANKS || rank < 0 || rank >= world)
     return fail(GACCUM_EINVAL, "world must be 1..%d and 0 <= rank < world (got world=%d rank=%d)", GACCUM_MAX_RANKS, world, rank);
-  int lo, hi;
-  shard_range(pl, world, rank, &lo, &hi, num_elements);
-  *tile_lo = lo;
-  *tile_hi = hi;
+  int bounds[GACCUM_MAX_RANKS + 1];
+  shard_bounds(pl, world, bounds);
+  *tile_lo = bounds[rank];
+  *tile_hi = bounds[rank + 1];
+  if (num_elements) {
+    int64_t e = 0;
+    for (int t = bounds[rank]; t < bounds[rank + 1]; ++t) e += pl->tiles[t].len;
+    *num_elements = e;
+  }
   return GACCUM_OK;
 }
 
-int gaccum_apply_dp(gaccum_plan* pl, const gaccum_dp_comm* comm, float* m, float* v,
+int64_t gaccum_dp_stage_elements(const gaccum_plan* pl, int32_t world) {
+  if (!pl) return fail(GACCUM_EINVAL, "plan is NULL");
+  if (world < 2 || world > GACCUM_MAX_RANKS) return fail(GACCUM_EINVAL, "world must be 2..%d", GACCUM_MAX_RANKS);
+  return stage_span(pl, world) * (world - 1);
+}
+
+extern "C++" {
+template <int CAP>
+static int do_apply_dp(gaccum_plan* pl, const gaccum_dp_comm* comm, const float* const* grads, float* m, float* v,
+                       const gaccum_step_args* a, uint32_t epoch, cudaStream_t st) {
+  DpParams<CAP>* prm = new (std::nothrow) DpParams<CAP>();
+  if (!prm) return fail(GACCUM_ENOMEM, "out of host memory");
+  const int W = comm->world;
+  for (int w = 0; w < W; ++w) {
+    prm->param[w] = comm->param_peers[w];
+    prm->stage[w] = comm->stage_peers[w];
+    prm->ctrl[w] = comm->ctrl_peers[w];
+  }
+  prm->tiles = pl->d_tiles;
+  prm->num_tiles = (int32_t)pl->tiles.size();
+  int bounds[GACCUM_MAX_RANKS + 1];
+  shard_bounds(pl, W, bounds);
+  for (int r = 0; r <= W; ++r) { prm->bounds[r] = bounds[r]; prm->shard_base32[r] = tile_soff32(pl, bounds[r]); }
+  prm->stage_span = stage_span(pl, W);
+  prm->accum = comm->accum;
+  prm->m = m;
+  prm->v = v;
+  prm->partials = pl->d_partials;
+  prm->stats = pl->d_stats;
+  prm->sync = pl->d_dp_sync;
+  prm->sc = make_scalars(pl->hp, a);
+  prm->rank = comm->rank;
+  prm->world = W;
+  prm->epoch = epoch;
+  for (int32_t t = 0; t < pl->T; ++t) prm->tab.g[t] = grads ? grads[t] : nullptr;
+  const void* fn = pl->hp.variant == GACCUM_ADAM ? (const void*)&dp_apply_kernel<1, CAP> : (const void*)&dp_apply_kernel<0, CAP>;
+  int grid = 0;
+  int rc = grid_for(pl, fn, &grid);
+  if (rc == GACCUM_OK) {
+    grid = std::max(1, std::min(grid, prm->num_tiles));
+    void* args[] = {(void*)prm};
+    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, 0, st);
+    if (e != cudaSuccess) rc = fail(GACCUM_ECUDA, "cudaLaunchCooperativeKernel(dp_apply_kernel) failed: %s", cudaGetErrorString(e));
+  }
+  delete prm;
+  return rc;
+}
+}  // extern "C++"
+
+int gaccum_apply_dp(gaccum_plan* pl, const gaccum_dp_comm* comm, const float* const* grads, float* m, float* v,
                     const gaccum_step_args* a, uint32_t epoch, gaccum_stream_t stream) {
   if (!comm) return fail(GACCUM_EINVAL, "comm is NULL");
   if (comm->world < 2 || comm->world > GACCUM_MAX_RANKS || comm->rank < 0 || comm->rank >= comm->world)
     return fail(GACCUM_EINVAL, "world must be 2..%d and 0 <= rank < world", GACCUM_MAX_RANKS);
   if (epoch == 0) return fail(GACCUM_EINVAL, "epoch must be non-zero");
   if (int rc = check_args(a)) return rc;
-  if (int rc = check_compute(pl, comm->accum_peers[comm->rank], m, v, true)) return rc;
+  if (int rc = check_compute(pl, comm->accum, m, v, true)) return rc;
   static_assert(kMaxRanks == GACCUM_MAX_RANKS && kCtrlBytes == GACCUM_DP_CTRL_BYTES, "header and kernel disagree");
-  DpParams prm{};
-  for (int w = 0; w < comm->world; ++w) {
-    if (!comm->accum_peers[w] || !comm->param_peers[w] || !comm->ctrl_peers[w] ||
-        !aligned16_host(comm->accum_peers[w]) || !aligned16_host(comm->param_peers[w]))
+  if (comm->stage_elements < stage_span(pl, comm->world) * (comm->world - 1))
+    return fail(GACCUM_EINVAL, "staging areas hold %lld elements, gaccum_dp_stage_elements() asks for %lld",
+                (long long)comm->stage_elements, (long long)(stage_span(pl, comm->world) * (comm->world - 1)));
+  for (int w = 0; w < comm->world; ++w)
+    if (!comm->param_peers[w] || !comm->stage_peers[w] || !comm->ctrl_peers[w] ||
+        !aligned16_host(comm->param_peers[w]) || !aligned16_host(comm->stage_peers[w]))
       return fail(GACCUM_EINVAL, "peer pointers of rank %d must be non-NULL and 16-byte aligned", w);
-    prm.accum[w] = comm->accum_peers[w];
-    prm.param[w] = comm->param_peers[w];
-    prm.ctrl[w] = comm->ctrl_peers[w];
-  }
   DeviceGuard guard(pl->device);
-  prm.tiles = pl->d_tiles;
-  prm.num_tiles = (int32_t)pl->tiles.size();
-  int lo, hi;
-  shard_range(pl, comm->world, comm->rank, &lo, &hi, nullptr);
-  prm.tile_lo = lo;
-  prm.tile_hi = hi;
-  prm.m = m;
-  prm.v = v;
-  prm.partials = pl->d_partials;
-  prm.stats = pl->d_stats;
-  prm.bcast = pl->d_bcast;
-  prm.tune = pl->tune;
-  prm.sc = make_scalars(pl->hp, a);
-  prm.rank = comm->rank;
-  prm.world = comm->world;
-  prm.epoch = epoch;
-  const void* fn = pl->hp.variant == GACCUM_ADAM ? (const void*)&dp_apply_kernel<1> : (const void*)&dp_apply_kernel<0>;
-  int grid = 0;
-  if (int rc = grid_for(pl, fn, &grid)) return rc;
-  grid = std::max(1, std::min(grid, prm.num_tiles));
-  void* args[] = {(void*)&prm};
-  CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, 0, (cudaStream_t)stream));
-  return GACCUM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  return pl->T <= kCapSmall ? do_apply_dp<kCapSmall>(pl, comm, grads, m, v, a, epoch, st)
+                            : do_apply_dp<kCapLarge>(pl, comm, grads, m, v, a, epoch, st);
+}
+
+int gaccum_step_dp(gaccum_plan* pl, const gaccum_dp_comm* comm, const float* const* grads, float* m, float* v,
+                   const gaccum_step_args* a, uint32_t epoch, gaccum_stream_t stream) {
+  if (!comm) return fail(GACCUM_EINVAL, "comm is NULL");
+  if (int rc = check_args(a)) return rc;
+  if (!grads) return fail(GACCUM_EINVAL, "grads is NULL");
+  if (gaccum_is_apply_step(a->global_step, a->accum_n)) return gaccum_apply_dp(pl, comm, grads, m, v, a, epoch, stream);
+  return accumulate_impl(pl, grads, comm->accum, a, stream);      // rank-local: no bytes cross NVLink
 }
 
 // ------------------------------------------------------------------------------------------
@@ -826,8 +838,8 @@ int gaccum_step_host(gaccum_host_session* s, const float* const* host_grads, flo
   }
   if (gather) {                                        // one launch for all small tensors: stage = G_host
     gaccum_step_args ga = *a;
-    int rc = pl->T <= kCapSmall ? do_accumulate_tab<kCapSmall>(pl, s->g_alias.data(), s->d_stage[b], &ga, s->h2d, kAccAssign)
-                                : do_accumulate_tab<kCapLarge>(pl, s->g_alias.data(), s->d_stage[b], &ga, s->h2d, kAccAssign);
+    int rc = pl->T <= kCapSmall ? do_accumulate_tab<kCapSmall>(pl, s->g_alias.data(), s->d_stage[b], &ga, s->h2d, kFlagAssign)
+                                : do_accumulate_tab<kCapLarge>(pl, s->g_alias.data(), s->d_stage[b], &ga, s->h2d, kFlagAssign);
     if (rc) return rc;
   }
   if (any_null)   // tensors without a gradient contribute nothing (optimization.py:132): stage zeros
@@ -870,13 +882,15 @@ int gaccum_host_session_slabs(gaccum_host_session* s, float** out) {
   return GACCUM_OK;
 }
 
-// Experiments only (not declared in gaccum.h): per-CTA timestamps of the last clip-apply launch.
+#ifdef GACCUM_EXPERIMENTS
+// Experiments build only (-DGACCUM_EXPERIMENTS, not declared in gaccum.h): per-CTA timestamps of the last clip-apply launch.
 extern "C" __attribute__((visibility("default"))) int gaccum_debug_read(gaccum_plan* pl, unsigned long long* out, int n) {
-  if (!pl || !pl->d_debug) return fail(GACCUM_EINVAL, "no debug buffer (set GACCUM_EXPERIMENTS=1 before creating the plan)");
+  if (!pl || !pl->d_debug) return fail(GACCUM_EINVAL, "no debug buffer");
   DeviceGuard guard(pl->device);
-  CUDA_TRY(cudaMemcpy(out, pl->d_debug, sizeof(unsigned long long) * (size_t)std::min(n, 4 * pl->max_grid), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(out, pl->d_debug, sizeof(unsigned long long) * (size_t)std::min(n, 16 * pl->max_grid), cudaMemcpyDeviceToHost));
   return GACCUM_OK;
 }
+#endif
 
 int gaccum_read_stats(gaccum_plan* pl, gaccum_stats* host_out, gaccum_stream_t stream) {
   if (!pl || !host_out) return fail(GACCUM_EINVAL, "bad arguments to gaccum_read_stats");

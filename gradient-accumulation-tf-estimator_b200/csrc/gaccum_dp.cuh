@@ -3,27 +3,33 @@
 // Replaces what reference distributedExample/04 does with MultiWorkerMirroredStrategy:
 // per-variable all-reduces on EVERY micro-step (04:55,58,70) followed by a replicated
 // apply (04:59-66).  Here every rank accumulates locally for the whole window and the exchange
-// happens once, inside the apply kernel, tile by tile:
+// happens once, inside the apply kernel.  Rank r OWNS the contiguous tile range
+// [bounds[r], bounds[r+1]) (equal element counts); m and v are only ever touched by their owner
+// (ZeRO-1 style).  The kernel is PUSH based -- remote STORES are fire-and-forget, remote loads would
+// have to cover ~2-3 us of NVLink latency with registers:
 //
-//   flags 0    (system-scope release/acquire words in symmetric memory, one block signals, every block
-//              waits): every rank's accumulator is final
-//   pass 1     rank r owns the tiles [tile_lo, tile_hi).  For each owned tile it LOADS THE TILE
-//              FROM EVERY RANK'S ACCUMULATOR over NVLink (peer pointers, fixed rank order
-//              0..W-1 => deterministic sum), writes the reduced a' into its own slab and
-//              reduces sum((a'/N)^2)                                  == reduce-scatter + norm
-//   flags 1    per-rank partial norms are exchanged through the control blocks; every rank
-//              adds the W partials in rank order => bit-identical gn and clip scale everywhere
-//   pass 2     clip + AdamWeightDecay/Adam on the owned tiles (m, v are only ever touched by
-//              their owner: ZeRO-1 style), and the new parameters are STORED INTO EVERY RANK'S
-//              PARAMETER SLAB over NVLink                               == all-gather
-//              meanwhile all non-owned tiles of the local accumulator are zeroed (:86-87)
-//   flags 2    all peers' parameter stores have landed before this kernel completes
+//   phase A   every tile of the model: x = a + G (the window's last local accumulate, folded in:
+//             optimization.py:81).  Owned tile: a <- x.  Foreign tile: x is STORED INTO THE OWNER'S
+//             STAGING AREA over NVLink (slot = source rank) and the local accumulator is zeroed
+//             (optimization.py:86-87).  Each rank starts its sweep at its right-hand neighbour's shard, so
+//             at any moment every owner receives from about one source.        == reduce-scatter, push
+//   flag 0    "all my pushes have landed" (block-completion counter -> system-scope release flags)
+//   phase B   owned tiles: a' = sum over ranks 0..W-1 of their contribution (own: a, others: staging),
+//             FIXED rank order => deterministic; a <- a'; partial sum((a'/N)^2)
+//   flag 1    per-rank partial norms travel with the flag; every rank adds the W partials in rank
+//             order => bit-identical gn and clip scale everywhere
+//   phase C   clip + AdamWeightDecay/Adam on the owned tiles, a <- 0, and the new parameters are STORED
+//             INTO EVERY RANK'S PARAMETER SLAB over NVLink                       == all-gather, push
+//   flag 2    all peers' parameter stores into my slab have landed before this kernel completes
 //   (a flag wait longer than 60 s means a dead peer: the kernel traps instead of hanging the GPU)
 //
-// NVLink bytes per rank and direction: 2 * (W-1)/W * 4P (the all-reduce lower bound); HBM
-// bytes of the update shrink to 1/W.  Parameters must live in one packed, peer-mapped slab
-// (plan offsets); the host side (PyTorch symmetric memory, NVSHMEM, cuMem IPC, ...) only
-// supplies the W base pointers.
+// NVLink bytes per rank and direction: 2 * (W-1)/W * 4P (the all-reduce lower bound); the update's HBM
+// bytes shrink to 1/W.  There is no grid-wide barrier: a phase ends when the last block of a rank bumps a
+// completion counter and raises that rank's flag in every control block; every block polls its own rank's
+// control block (local memory).  All blocks must be co-resident (cooperative launch guarantees it).
+// Parameters must live in one packed, peer-mapped slab (plan offsets); the host side (PyTorch symmetric
+// memory, NVSHMEM, cuMem IPC, ...) only supplies the W base pointers of the parameter slabs, staging areas
+// and control blocks.
 #pragma once
 
 #include "gaccum_kernels.cuh"
@@ -39,47 +45,58 @@ constexpr int kCtrlNormByteOffset = 128;
 constexpr int kCtrlBytes = 256;
 constexpr unsigned long long kDpTimeoutNs = 60ull * 1000 * 1000 * 1000;   // a flag wait longer than 60 s is a dead peer
 
+template <int CAP>
+struct GradTable {
+  const float* g[CAP];
+};
+
+template <int CAP>
 struct DpParams {
   const TileDesc* tiles;
-  int32_t num_tiles, tile_lo, tile_hi;
+  int32_t num_tiles;
+  int32_t bounds[kMaxRanks + 1];        // tile range of every rank's shard
+  uint32_t shard_base32[kMaxRanks + 1]; // slab offset (units of 32 elements) at which every shard starts
+  int64_t stage_span;                   // elements per source region of a staging area (multiple of 32)
+  float* accum;                         // local accumulator slab
   float* m;
   float* v;
   double* partials;
   float* stats;
-  float* bcast;          // plan-owned: {scale, gn}
-  uint32_t tune;
+  uint32_t* sync;                       // 3 block-completion counters, zero between launches
   Scalars sc;
   int32_t rank, world;
   uint32_t epoch;
-  float* accum[kMaxRanks];
   float* param[kMaxRanks];
+  float* stage[kMaxRanks];
   uint32_t* ctrl[kMaxRanks];
+  GradTable<CAP> tab;
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-// Peer accumulator data is read exactly once per kernel, after flag round 0 (every block polls its
-// own rank's control block and issues one acquire fence at system scope), L1 is invalidated at every
-// launch and peer lines bypass the local L2: a plain LDG.128 is coherent here and lets the compiler
-// keep all W x kUnroll x tiles-per-iteration loads in flight (NVLink latency is ~2 us; ordering them
-// would serialise it).
-__device__ __forceinline__ float4 ld_peer(const float4* p) { return *p; }
-__device__ __forceinline__ float ld_peer(const float* p) { return *p; }
 
-// Cross-GPU flags.  Signalling is done by ONE block (thread t < W writes rank t's control block with
-// release semantics at system scope); waiting is done by EVERY block on its own rank's control
-// block (local memory), so no grid-wide barrier is needed to fan the news out.
-__device__ __forceinline__ void dp_signal(const DpParams& prm, int phase) {
-  const int t = threadIdx.x;
-  if (t < prm.world) st_release_sys(prm.ctrl[t] + phase * kMaxRanks + prm.rank, prm.epoch);
+// End of a phase on this rank: every thread orders its (local and remote) stores at system scope, the block
+// bumps the phase's completion counter, and the LAST block to arrive raises this rank's flag in every
+// rank's control block (its own included).  `extra` lets the last block publish the norm first.
+template <int CAP, typename F>
+__device__ __forceinline__ void dp_phase_done(const DpParams<CAP>& prm, int phase, F&& extra) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const bool last = atomicAdd(prm.sync + phase, 1u) == gridDim.x - 1;
+    if (last) {
+      __threadfence_system();            // acquire side of the counter chain
+      prm.sync[phase] = 0;               // re-arm for the next launch (nobody touches it again in this one)
+      extra();
+      for (int w = 0; w < prm.world; ++w) st_release_sys(prm.ctrl[w] + phase * kMaxRanks + prm.rank, prm.epoch);
+    }
+  }
 }
-__device__ __forceinline__ void dp_wait(const DpParams& prm, int phase) {
+// Every block: wait until all W ranks have raised `phase` for this epoch (polling this rank's own control block)
+template <int CAP>
+__device__ __forceinline__ void dp_wait(const DpParams<CAP>& prm, int phase) {
   const int t = threadIdx.x;
   if (t < prm.world) {
     const uint32_t* mine = prm.ctrl[prm.rank] + phase * kMaxRanks + t;
@@ -103,88 +120,125 @@ __device__ __forceinline__ void dp_wait(const DpParams& prm, int phase) {
   __syncthreads();
 }
 
-// pass 1 on TPI owned tiles at once: a' = sum_w a_w (rank order), stored locally; returns
-// acc + sum((a'/N)^2).  TPI x kUnroll x W 128-bit loads are in flight per thread: NVLink reads
-// have ~2-3 us latency, so ~16 outstanding vectors per thread are needed to fill the links.
-template <int TPI>
-__device__ __forceinline__ float dp_reduce_tiles(const TileDesc (&d)[TPI], const int ntile, const DpParams& prm,
-                                                 float acc, const uint64_t pol) {
-  const uint32_t tid = threadIdx.x;
-  const float nf = prm.sc.nf, inv_nf = prm.sc.inv_nf;
-  const int W = prm.world;
-  float4 part[TPI][kUnroll][kMaxRanks / (TPI > 1 ? (TPI > 2 ? 4 : 2) : 1)];
-  constexpr int WCAP = kMaxRanks / (TPI > 1 ? (TPI > 2 ? 4 : 2) : 1);   // TPI=4 -> W<=2, TPI=2 -> W<=4, TPI=1 -> W<=8
+template <int CAP>
+__device__ __forceinline__ int dp_owner(const DpParams<CAP>& prm, int t) {
+  int o = 0;
 #pragma unroll
-  for (int j = 0; j < TPI; ++j) {
-    if (j < ntile) {
-      const size_t soff = (size_t)d[j].soff32 * kSlabAlign;
-      const uint32_t nvec = d[j].len >> 2;
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        const uint32_t i = u * kThreads + tid;
-        if (i < nvec) {
-#pragma unroll
-          for (int w = 0; w < WCAP; ++w)
-            if (w < W) part[j][u][w] = ld_peer(reinterpret_cast<const float4*>(prm.accum[w] + soff) + i);
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < TPI; ++j) {
-    if (j < ntile) {
-      const size_t soff = (size_t)d[j].soff32 * kSlabAlign;
-      const uint32_t len = d[j].len, nvec = len >> 2;
-      float4* mine = reinterpret_cast<float4*>(prm.accum[prm.rank] + soff);
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        const uint32_t i = u * kThreads + tid;
-        if (i < nvec) {
-          float4 s = part[j][u][0];
-#pragma unroll
-          for (int w = 1; w < WCAP; ++w)
-            if (w < W) {
-              s.x = __fadd_rn(s.x, part[j][u][w].x); s.y = __fadd_rn(s.y, part[j][u][w].y);
-              s.z = __fadd_rn(s.z, part[j][u][w].z); s.w = __fadd_rn(s.w, part[j][u][w].w);
-            }
-          st_policy(mine + i, s, pol);
-          const float nx = normalize(s.x, nf, inv_nf), ny = normalize(s.y, nf, inv_nf), nz = normalize(s.z, nf, inv_nf), nw = normalize(s.w, nf, inv_nf);
-          acc = fmaf(nx, nx, acc); acc = fmaf(ny, ny, acc); acc = fmaf(nz, nz, acc); acc = fmaf(nw, nw, acc);
-        }
-      }
-      const uint32_t i = (nvec << 2) + tid;
-      if (i < len) {
-        float s = ld_peer(prm.accum[0] + soff + i);
-        for (int w = 1; w < W; ++w) s = __fadd_rn(s, ld_peer(prm.accum[w] + soff + i));
-        prm.accum[prm.rank][soff + i] = s;
-        const float n = normalize(s, nf, inv_nf);
-        acc = fmaf(n, n, acc);
-      }
-    }
-  }
-  return acc;
+  for (int w = 1; w < kMaxRanks; ++w) o += (w < prm.world && t >= prm.bounds[w]) ? 1 : 0;
+  return o;
 }
 
-template <int TPI>
-__device__ __forceinline__ double dp_pass1(const DpParams& prm, const uint64_t pol) {
-  double acc = 0.0;
-  const int lo = prm.tile_lo, hi = prm.tile_hi, G = (int)gridDim.x;
-  for (int t0 = lo + (int)blockIdx.x; t0 < hi; t0 += TPI * G) {
-    TileDesc d[TPI];
-    int n = 0;
-#pragma unroll
-    for (int j = 0; j < TPI; ++j)
-      if (t0 + j * G < hi) { d[j] = prm.tiles[t0 + j * G]; n = j + 1; }
-    acc += (double)dp_reduce_tiles<TPI>(d, n, prm, 0.f, pol);
-  }
-  return acc;
-}
-
-// pass 2 on one owned tile: update from the local reduced a', broadcast p' to every rank
-template <int VARIANT>
-__device__ __forceinline__ void dp_update_tile(const TileDesc d, const DpParams& prm, const float s) {
+// ---- phase A: one tile.  x = a + G; owned -> a = x (kept for phase B), foreign -> owner's staging, a = 0 ----
+template <int CAP>
+__device__ __forceinline__ void dp_push_tile(const TileDesc d, const int t, const DpParams<CAP>& prm, const uint64_t pol) {
+  const float* __restrict__ g = prm.tab.g[d.tensor_flags & 0x7fffffffu];
+  if (g) g += d.toff;
   const size_t soff = (size_t)d.soff32 * kSlabAlign;
-  float* __restrict__ a = prm.accum[prm.rank] + soff;
+  float* __restrict__ a = prm.accum + soff;
+  const int owner = dp_owner(prm, t);
+  const bool mine = owner == prm.rank;
+  float* __restrict__ dst = nullptr;
+  if (!mine) {
+    const int slot = prm.rank < owner ? prm.rank : prm.rank - 1;
+    dst = prm.stage[owner] + (size_t)slot * prm.stage_span + (soff - (size_t)prm.shard_base32[owner] * kSlabAlign);
+  }
+  const uint32_t len = d.len, tid = threadIdx.x;
+  if (mine && g == nullptr) return;                       // nothing to add, nothing to send
+  if (g == nullptr || aligned16(g)) {
+    const uint32_t nvec = len >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4* a4 = reinterpret_cast<float4*>(a);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    float4 va[kUnroll], vg[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint32_t i = u * kThreads + tid;
+      if (i < nvec) { va[u] = __ldcs(a4 + i); if (g) vg[u] = ld_stream(g4 + i); }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint32_t i = u * kThreads + tid;
+      if (i < nvec) {
+        if (g) {
+          va[u].x = __fadd_rn(va[u].x, vg[u].x); va[u].y = __fadd_rn(va[u].y, vg[u].y);
+          va[u].z = __fadd_rn(va[u].z, vg[u].z); va[u].w = __fadd_rn(va[u].w, vg[u].w);
+        }
+        if (mine) st_policy(a4 + i, va[u], pol);
+        else { d4[i] = va[u]; __stcs(a4 + i, make_float4(0.f, 0.f, 0.f, 0.f)); }
+      }
+    }
+    const uint32_t i = (nvec << 2) + tid;
+    if (i < len) {
+      float x = a[i];
+      if (g) x = __fadd_rn(x, ld_stream(g + i));
+      if (mine) a[i] = x; else { dst[i] = x; a[i] = 0.f; }
+    }
+  } else {
+    for (uint32_t i = tid; i < len; i += kThreads) {
+      const float x = __fadd_rn(a[i], ld_stream(g + i));
+      if (mine) a[i] = x; else { dst[i] = x; a[i] = 0.f; }
+    }
+  }
+}
+
+// ---- phase B: one owned tile.  a' = sum_w contribution_w in rank order; returns sum((a'/N)^2) ----
+template <int CAP>
+__device__ __forceinline__ float dp_reduce_tile(const TileDesc d, const DpParams<CAP>& prm, const uint64_t pol) {
+  const size_t soff = (size_t)d.soff32 * kSlabAlign;
+  const size_t rel = soff - (size_t)prm.shard_base32[prm.rank] * kSlabAlign;
+  float* __restrict__ a = prm.accum + soff;
+  const float* __restrict__ stg = prm.stage[prm.rank] + rel;
+  const int64_t span = prm.stage_span;
+  const uint32_t len = d.len, tid = threadIdx.x, nvec = len >> 2;
+  const float nf = prm.sc.nf, inv_nf = prm.sc.inv_nf;
+  const int W = prm.world, R = prm.rank;
+  float acc = 0.f;
+  float4* a4 = reinterpret_cast<float4*>(a);
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    const uint32_t i = u * kThreads + tid;
+    if (i < nvec) {
+      float4 part[kMaxRanks];
+#pragma unroll
+      for (int w = 0; w < kMaxRanks; ++w) {
+        if (w < W) {
+          // contributions arrived from other SMs / other GPUs during this kernel: read them at L2
+          const float4* src = (w == R) ? (a4 + i) : reinterpret_cast<const float4*>(stg + (size_t)(w < R ? w : w - 1) * span) + i;
+          part[w] = __ldcg(src);
+        }
+      }
+      float4 s = part[0];
+#pragma unroll
+      for (int w = 1; w < kMaxRanks; ++w) {
+        if (w < W) {
+          s.x = __fadd_rn(s.x, part[w].x); s.y = __fadd_rn(s.y, part[w].y);
+          s.z = __fadd_rn(s.z, part[w].z); s.w = __fadd_rn(s.w, part[w].w);
+        }
+      }
+      st_policy(a4 + i, s, pol);
+      const float nx = normalize(s.x, nf, inv_nf), ny = normalize(s.y, nf, inv_nf), nz = normalize(s.z, nf, inv_nf), nw = normalize(s.w, nf, inv_nf);
+      acc = fmaf(nx, nx, acc); acc = fmaf(ny, ny, acc); acc = fmaf(nz, nz, acc); acc = fmaf(nw, nw, acc);
+    }
+  }
+  const uint32_t i = (nvec << 2) + tid;
+  if (i < len) {
+    float s = 0.f;
+    for (int w = 0; w < W; ++w) {
+      const float x = __ldcg((w == R) ? (a + i) : (stg + (size_t)(w < R ? w : w - 1) * span + i));
+      s = (w == 0) ? x : __fadd_rn(s, x);
+    }
+    a[i] = s;
+    const float n = normalize(s, nf, inv_nf);
+    acc = fmaf(n, n, acc);
+  }
+  return acc;
+}
+
+// ---- phase C: one owned tile.  update from the reduced a', broadcast p' to every rank ----
+template <int VARIANT, int CAP>
+__device__ __forceinline__ void dp_update_tile(const TileDesc d, const DpParams<CAP>& prm, const float s) {
+  const size_t soff = (size_t)d.soff32 * kSlabAlign;
+  float* __restrict__ a = prm.accum + soff;
   float* __restrict__ m = prm.m + soff;
   float* __restrict__ v = prm.v + soff;
   const float* __restrict__ p = prm.param[prm.rank] + soff;
@@ -204,7 +258,7 @@ __device__ __forceinline__ void dp_update_tile(const TileDesc d, const DpParams&
 #pragma unroll
   for (int u = 0; u < kUnroll; ++u) {
     const uint32_t i = u * kThreads + tid;
-    if (i < nvec) { va[u] = __ldcs(a4 + i); vp[u] = __ldcs(p4 + i); vm[u] = __ldcs(m4 + i); vv[u] = __ldcs(v4 + i); }
+    if (i < nvec) { va[u] = __ldcg(a4 + i); vp[u] = __ldcs(p4 + i); vm[u] = __ldcs(m4 + i); vv[u] = __ldcs(v4 + i); }
   }
 #pragma unroll
   for (int u = 0; u < kUnroll; ++u) {
@@ -222,74 +276,53 @@ __device__ __forceinline__ void dp_update_tile(const TileDesc d, const DpParams&
   const uint32_t i = (nvec << 2) + tid;
   if (i < len) {
     float px = p[i], mx = m[i], vx = v[i];
-    elem(a[i], px, mx, vx);
+    elem(__ldcg(a + i), px, mx, vx);
     m[i] = mx; v[i] = vx; a[i] = 0.f;
     for (int w = 0; w < W; ++w) prm.param[w][soff + i] = px;
   }
 }
 
-__device__ __forceinline__ void dp_zero_tile(const TileDesc d, const DpParams& prm) {
-  float* a = prm.accum[prm.rank] + (size_t)d.soff32 * kSlabAlign;
-  const uint32_t len = d.len, tid = threadIdx.x, nvec = len >> 2;
-  float4* a4 = reinterpret_cast<float4*>(a);
-#pragma unroll
-  for (int u = 0; u < kUnroll; ++u) {
-    const uint32_t i = u * kThreads + tid;
-    if (i < nvec) __stcs(a4 + i, make_float4(0.f, 0.f, 0.f, 0.f));
-  }
-  const uint32_t i = (nvec << 2) + tid;
-  if (i < len) a[i] = 0.f;
-}
-
-template <int VARIANT>
-__global__ void __launch_bounds__(kThreads)
-dp_apply_kernel(const __grid_constant__ DpParams prm) {
+template <int VARIANT, int CAP>
+__global__ void __launch_bounds__(kThreads, 4)
+dp_apply_kernel(const __grid_constant__ DpParams<CAP> prm) {
   __shared__ double red[kThreads / 32];
   __shared__ float s_bcast[2];
-  cg::grid_group grid = cg::this_grid();
   const uint64_t pol = policy_evict_last();
-  const int lo = prm.tile_lo, hi = prm.tile_hi, nt = prm.num_tiles;
+  const int W = prm.world, R = prm.rank, nt = prm.num_tiles, G = (int)gridDim.x;
+  const int lo = prm.bounds[R], hi = prm.bounds[R + 1];
 
-  // ---- flag 0: my accumulators are final (stream order: the local accumulate ran before this
-  //      kernel); every block waits until that is true of every rank ------------------------------
-  if (blockIdx.x == 0) dp_signal(prm, 0);
+  // ---- phase A: local accumulate + reduce-scatter by pushes.  The sweep starts at the right-hand
+  //      neighbour's shard: owner (R+1+j) % W is being written by rank R while rank R+1 writes (R+2+j) % W ... ----
+  {
+    const int start = prm.bounds[(R + 1) % W];
+    for (int q = (int)blockIdx.x; q < nt; q += G) {
+      int t = q + start;
+      if (t >= nt) t -= nt;
+      dp_push_tile(prm.tiles[t], t, prm, pol);
+    }
+  }
+  dp_phase_done(prm, 0, [] {});
   dp_wait(prm, 0);
 
-  // ---- pass 1: reduce-scatter over peer loads + norm partial -------------------------------------
+  // ---- phase B: deterministic reduction of the owned shard + norm partial -------------------------
   double acc = 0.0;
-  if (!(prm.tune & kTuneSkipPass1)) {
-    if (prm.world <= 2) acc = dp_pass1<4>(prm, pol);
-    else if (prm.world <= 4) acc = dp_pass1<2>(prm, pol);
-    else acc = dp_pass1<1>(prm, pol);
-  }
+  for (int t = lo + (int)blockIdx.x; t < hi; t += G) acc += (double)dp_reduce_tile(prm.tiles[t], prm, pol);
   const double part = block_reduce_to_double(acc, red);
   if (threadIdx.x == 0) prm.partials[blockIdx.x] = part;
-  grid.sync();                     // gpu-scope: a' (local, read only by this rank) and the partials are visible
-
-  // ---- flag 1: this rank's partial norm goes to every rank (itself included) ---------------------
-  if (blockIdx.x == 0) {
-    __shared__ double s_tot;
-    if (threadIdx.x < 32) {
-      double tot = 0.0;
-      for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) tot += __ldcg(prm.partials + i);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-      if (threadIdx.x == 0) s_tot = tot;
+  dp_phase_done(prm, 1, [&] {
+    // last block of this rank: per-block partials in block order -> this rank's partial norm -> every rank
+    double tot = 0.0;
+    for (int i = 0; i < G; ++i) tot += __ldcg(prm.partials + i);
+    for (int w = 0; w < W; ++w) {
+      double* slot = reinterpret_cast<double*>(reinterpret_cast<char*>(prm.ctrl[w]) + kCtrlNormByteOffset) + R;
+      asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(slot), "d"(tot) : "memory");
     }
-    __syncthreads();
-    if ((int)threadIdx.x < prm.world) {
-      double* slot = reinterpret_cast<double*>(reinterpret_cast<char*>(prm.ctrl[threadIdx.x]) + kCtrlNormByteOffset) + prm.rank;
-      asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(slot), "d"(s_tot) : "memory");
-    }
-    dp_signal(prm, 1);             // same thread: the release store orders the partial before the flag
-  }
-  // every block: wait for all W partials (also proves every rank finished READING my accumulators),
-  // then add them in rank order -> bit-identical gn and s on every block of every rank
+  });
   dp_wait(prm, 1);
   if (threadIdx.x == 0) {
-    const double* slots = reinterpret_cast<const double*>(reinterpret_cast<const char*>(prm.ctrl[prm.rank]) + kCtrlNormByteOffset);
+    const double* slots = reinterpret_cast<const double*>(reinterpret_cast<const char*>(prm.ctrl[R]) + kCtrlNormByteOffset);
     double tot = 0.0;
-    for (int w = 0; w < prm.world; ++w) {
+    for (int w = 0; w < W; ++w) {
       double x;
       asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(x) : "l"(slots + w) : "memory");
       tot += x;
@@ -304,17 +337,11 @@ dp_apply_kernel(const __grid_constant__ DpParams prm) {
   __syncthreads();
   const float s = s_bcast[0];
 
-  // ---- pass 2: sharded update + all-gather by peer stores; zero everything I do not own ---------
-  if (!(prm.tune & kTuneSkipPass2))
-    for (int t = hi - 1 - (int)blockIdx.x; t >= lo; t -= (int)gridDim.x) dp_update_tile<VARIANT>(prm.tiles[t], prm, s);
-  if (!(prm.tune & kTuneSkipZero))
-    for (int t = (int)blockIdx.x; t < nt; t += (int)gridDim.x)
-      if (t < lo || t >= hi) dp_zero_tile(prm.tiles[t], prm);
-  __threadfence_system();
-  grid.sync();
-
-  // ---- flag 2: every peer's parameter stores into my slab are complete before the kernel ends ----
-  if (blockIdx.x == 0) { dp_signal(prm, 2); dp_wait(prm, 2); }
+  // ---- phase C: sharded update + all-gather by pushes (same tile -> block mapping as phase B) -------
+  for (int t = lo + (int)blockIdx.x; t < hi; t += G) dp_update_tile<VARIANT>(prm.tiles[t], prm, s);
+  dp_phase_done(prm, 2, [] {});
+  // every peer's parameter stores into my slab are complete before the kernel ends
+  if (blockIdx.x == 0) dp_wait(prm, 2);
 }
 
 }  // namespace gaccum

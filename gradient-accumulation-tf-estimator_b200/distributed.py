@@ -24,6 +24,7 @@ import torch.distributed as dist
 
 class DataParallelTrainOp:
     """Wraps an engine exposing accumulate_only / apply_only / run / accum / N / global_step."""
+    launches_per_apply = 2      # local accumulate + apply (the all-reduce between them is NCCL's kernel)
 
     def __init__(self, engine, process_group=None):
         self.engine = engine
@@ -50,16 +51,18 @@ class FusedDataParallelTrainOp:
     """The data-parallel train_op with the exchange INSIDE the apply kernel (csrc/gaccum_dp.cuh).
 
     Parameters are moved into one packed slab in NVLink peer-mapped symmetric memory (the tensors
-    passed in are re-pointed at views of it, so the model keeps working unchanged); the accumulator
-    slab and a 256-byte control block live there too.  PyTorch's symmetric-memory allocator is only
-    the plumbing that maps every rank's buffers into every process -- the kernel does the
-    reduce-scatter (peer loads), the norm exchange and the all-gather (peer stores) itself.
-    Accumulate steps are rank-local: zero bytes cross NVLink until the apply step (vs one
-    all-reduce per variable per micro-step in 04:55,58,70).
+    passed in are re-pointed at views of it, so the model keeps working unchanged); a staging area
+    (W-1 shard-sized regions) and a 256-byte control block live there too.  PyTorch's symmetric-memory
+    allocator is only the plumbing that maps every rank's buffers into every process -- the kernel does
+    the reduce-scatter (peer stores into the owner's staging area), the norm exchange and the
+    all-gather (peer stores into every parameter slab) itself, in ONE launch that also performs the
+    window's last local ``a += G``.  Accumulate steps are rank-local: zero bytes cross NVLink until
+    the apply step (vs one all-reduce per variable per micro-step in 04:55,58,70).
 
     m / v are sharded: each rank holds valid Adam moments only for the tiles it owns
     (``plan.dp_shard_range``); ``gather_state()`` rebuilds full copies for checkpoints.
     """
+    launches_per_apply = 1
 
     def __init__(self, params: Sequence[torch.Tensor], names: Sequence[str], hp, accum_n: int, lr_fn,
                  process_group=None, exclude_from_weight_decay=("LayerNorm", "layer_norm", "bias"),
@@ -77,35 +80,34 @@ class FusedDataParallelTrainOp:
         dev = params[0].device
         layout = _lib.Plan([p.numel() for p in params], None, hp, device=-1)
         n = max(layout.padded_size, 32)
+        stage_n = layout.dp_stage_elements(self.world)
         self.param_slab = symm.empty(n, dtype=torch.float32, device=dev)
-        self.accum_slab = symm.empty(n, dtype=torch.float32, device=dev)
+        self.stage = symm.empty(stage_n, dtype=torch.float32, device=dev)
         self.ctrl = symm.empty(_lib.DP_CTRL_BYTES // 4, dtype=torch.int32, device=dev)
-        self.param_slab.zero_(); self.accum_slab.zero_(); self.ctrl.zero_()
-        views = []
+        self.param_slab.zero_(); self.stage.zero_(); self.ctrl.zero_()
         with torch.no_grad():
             for p, o in zip(params, layout.offsets):
                 view = self.param_slab[o:o + p.numel()].view(p.shape)
                 view.copy_(p)
                 p.data = view                      # the caller's tensors now alias the packed slab
-                views.append(p.data)
         gname = self.group.group_name
-        self._handles = [symm.rendezvous(t, gname) for t in (self.param_slab, self.accum_slab, self.ctrl)]
-        hp_, ha_, hc_ = self._handles
+        self._handles = [symm.rendezvous(t, gname) for t in (self.param_slab, self.stage, self.ctrl)]
+        hp_, hs_, hc_ = self._handles
+        self.engine = GaccumTrainOp(list(params), names, hp, accum_n, lr_fn, exclude_from_weight_decay, global_step)
+        self.plan = self.engine.plan
         self.comm = _lib.DpComm()
         self.comm.rank, self.comm.world = self.rank, self.world
+        self.comm.accum = self.engine.accum.data_ptr()        # private: peers never touch the accumulators
+        self.comm.stage_elements = stage_n
         for w in range(self.world):
             self.comm.param_peers[w] = int(hp_.buffer_ptrs[w])
-            self.comm.accum_peers[w] = int(ha_.buffer_ptrs[w])
+            self.comm.stage_peers[w] = int(hs_.buffer_ptrs[w])
             self.comm.ctrl_peers[w] = int(hc_.buffer_ptrs[w])
         if os.environ.get("GACCUM_DP_LOCAL_VA", "1") == "1":
             # own buffers through their ordinary local mapping, not the peer-aperture alias
             self.comm.param_peers[self.rank] = self.param_slab.data_ptr()
-            self.comm.accum_peers[self.rank] = self.accum_slab.data_ptr()
+            self.comm.stage_peers[self.rank] = self.stage.data_ptr()
             self.comm.ctrl_peers[self.rank] = self.ctrl.data_ptr()
-        self.peer_ptr_info = {"accum_local_va": self.accum_slab.data_ptr(), "accum_symm_va": int(ha_.buffer_ptrs[self.rank])}
-        self.engine = GaccumTrainOp(list(params), names, hp, accum_n, lr_fn, exclude_from_weight_decay,
-                                    global_step, accum=self.accum_slab)
-        self.plan = self.engine.plan
         self.tile_lo, self.tile_hi, self.owned_elements = self.plan.dp_shard_range(self.world, self.rank)
         self.epoch = 0
         self.exchanges = 0
@@ -126,14 +128,13 @@ class FusedDataParallelTrainOp:
         e = self.engine
         g = e.global_step
         if (g % e.N) != 0:
-            return e.run_bound(grad_table, stream)
+            return e.run_bound(grad_table, stream)            # rank-local accumulate (04:58 without the all-reduce)
         if stream is None:
             stream = torch.cuda.current_stream(e.device).cuda_stream
         from ._lib import StepArgs
         lr = e.lr_fn(g)
-        e.plan.accumulate(grad_table, e._accum_ptr, stream)            # 04:58, rank-local
         self.epoch += 1
-        e.plan.apply_dp(self.comm, e._m_ptr, e._v_ptr,
+        e.plan.apply_dp(self.comm, grad_table, e._m_ptr, e._v_ptr,
                         StepArgs(g, e.N, 0, lr, e.beta1_power, e.beta2_power, 0.0), self.epoch, stream)
         self.exchanges += 1
         e._after(True, lr)

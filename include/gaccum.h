@@ -13,7 +13,8 @@
  *   - the caller owns every device buffer (params, grads, accum, m, v); the library owns only
  *     the opaque plan (static tile table, decay mask, per-CTA partial buffer, stats block).
  *   - all hot calls are asynchronous on the caller's CUDA stream, never synchronise the host,
- *     and launch exactly one kernel.  A plan may be used on one stream at a time.
+ *     and launch exactly one kernel (the data-parallel apply step included).  A plan may be used
+ *     on one stream at a time.
  *   - there is NO CPU fallback: without a CUDA device every compute call fails with
  *     GACCUM_ENODEVICE.  A plan created with device = -1 is layout-only (offset queries).
  *   - all state is IEEE fp32; arithmetic follows the reference's un-fused op order with
@@ -35,7 +36,7 @@ extern "C" {
 #define GACCUM_API
 #endif
 
-#define GACCUM_VERSION 100 /* 0.1.0 */
+#define GACCUM_VERSION 200 /* 0.2.0: TMA-fed clip-apply, push-based data-parallel apply (gaccum_dp_comm changed) */
 
 /* error codes */
 #define GACCUM_OK 0
@@ -148,35 +149,48 @@ GACCUM_API int gaccum_step_packed(gaccum_plan* plan, const float* grad_slab, flo
 /* ---- data parallel: the apply step fused with its exchange over NVLink peer memory ------- */
 /* Replaces reference distributedExample/04's MultiWorkerMirroredStrategy wiring: accumulators
  * with aggregation=SUM (04:55) all-reduced per variable on every micro-step (04:58,70) and a
- * replicated apply (04:59-66).  Each rank accumulates locally (gaccum_accumulate / gaccum_step)
- * and calls gaccum_apply_dp on the apply step: ONE kernel that reduce-scatters the accumulators
- * by peer loads, exchanges the partial global norms, updates the tiles the rank owns and
- * all-gathers the new parameters by peer stores (csrc/gaccum_dp.cuh).  The loss is expected to be
+ * replicated apply (04:59-66).  Each rank calls gaccum_step_dp once per micro-step: accumulate
+ * steps are the rank-local accumulate kernel (no bytes cross NVLink); the apply step is ONE kernel
+ * (csrc/gaccum_dp.cuh) that adds the last gradient, pushes every foreign tile of a + G into its
+ * owner's staging area (reduce-scatter by peer stores), reduces its own shard in fixed rank order,
+ * exchanges the partial global norms, updates the tiles the rank owns and pushes the new parameters
+ * into every rank's parameter slab (all-gather by peer stores).  The loss is expected to be
  * pre-divided by the number of workers, as 04:46 does. */
 #define GACCUM_MAX_RANKS 8
 #define GACCUM_DP_CTRL_BYTES 256
 typedef struct gaccum_dp_comm {
   int32_t rank;
   int32_t world; /* 2..GACCUM_MAX_RANKS */
+  /* this rank's packed fp32 accumulator slab (gaccum_padded_size floats); private, never peer-accessed */
+  float* accum;
   /* Base device pointers of every rank's buffers, all mapped into this process (symmetric
    * memory / CUDA IPC / cuMem fabric handles); entry [rank] is the local buffer.
-   *   accum_peers: packed fp32 accumulator slabs (gaccum_padded_size floats)
-   *   param_peers: packed fp32 parameter slabs, same layout (gaccum_offsets)
+   *   param_peers: packed fp32 parameter slabs, slab layout (gaccum_offsets)
+   *   stage_peers: staging areas of gaccum_dp_stage_elements() floats (contents are scratch)
    *   ctrl_peers : GACCUM_DP_CTRL_BYTES control blocks, zero-initialised once */
-  float* accum_peers[GACCUM_MAX_RANKS];
   float* param_peers[GACCUM_MAX_RANKS];
+  float* stage_peers[GACCUM_MAX_RANKS];
   uint32_t* ctrl_peers[GACCUM_MAX_RANKS];
+  int64_t stage_elements; /* floats each staging area holds */
 } gaccum_dp_comm;
 /* tiles [*tile_lo, *tile_hi) and the element count rank `rank` of `world` owns */
 GACCUM_API int gaccum_dp_shard_range(const gaccum_plan* plan, int32_t world, int32_t rank,
                                      int32_t* tile_lo, int32_t* tile_hi, int64_t* num_elements);
-/* `epoch` must be non-zero and different from the previous call's (e.g. a call counter), and the
- * same on every rank.  m / v: local slabs; only the owned range is read or written.
+/* floats every rank's staging area must hold for `world` ranks: (world-1) x the widest shard */
+GACCUM_API int64_t gaccum_dp_stage_elements(const gaccum_plan* plan, int32_t world);
+/* One micro-step on this rank (04:48-74).  grads[i]: this rank's gradient of tensor i (device, scattered,
+ * NULL = none).  `epoch` must be non-zero, different from the previous apply's (e.g. an apply counter)
+ * and the same on every rank.  m / v: local slabs; only the owned range is read or written.
  * All `world` ranks must call this for the same step; the call is asynchronous on `stream`.
- * If a peer never reaches the matching call (crashed rank, mismatched epoch) the kernel traps after
+ * If a peer never reaches the matching apply (crashed rank, mismatched epoch) the kernel traps after
  * 60 s of waiting and the failure surfaces as a CUDA error on the next runtime call. */
-GACCUM_API int gaccum_apply_dp(gaccum_plan* plan, const gaccum_dp_comm* comm, float* m, float* v,
-                               const gaccum_step_args* args, uint32_t epoch, gaccum_stream_t stream);
+GACCUM_API int gaccum_step_dp(gaccum_plan* plan, const gaccum_dp_comm* comm, const float* const* grads,
+                              float* m, float* v, const gaccum_step_args* args, uint32_t epoch,
+                              gaccum_stream_t stream);
+/* the apply branch alone (args->global_step is not consulted) */
+GACCUM_API int gaccum_apply_dp(gaccum_plan* plan, const gaccum_dp_comm* comm, const float* const* grads,
+                               float* m, float* v, const gaccum_step_args* args, uint32_t epoch,
+                               gaccum_stream_t stream);
 
 /* ---- host-buffer session: the same train_op for a caller whose tensors live in HOST memory -- */
 /* (e.g. the reference run with CPU placement, distributedExample/02 "1 worker CPU").  The session

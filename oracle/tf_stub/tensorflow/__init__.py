@@ -117,6 +117,8 @@ def _realdiv(x, y):
 def convert_to_tensor(v, dtype=None, name=None):
     if isinstance(v, Tensor):
         return v
+    if v is None:
+        raise ValueError("None values not supported.")          # what TF's make_tensor_proto raises
     if dtype is None:
         if isinstance(v, bool):
             dtype = bool_
@@ -392,6 +394,80 @@ class Optimizer:
         self._name = name
 
 
+class AdamOptimizer(Optimizer):
+    """``tf.train.AdamOptimizer`` / ``tf.compat.v1.train.AdamOptimizer`` as TF 1.15 runs it on dense fp32
+    variables (python/training/adam.py + core/kernels/training_ops.cc, ApplyAdam, use_nesterov=False).
+    RESTATEMENT of TensorFlow (not of the reference): listed in tests/golden/MANIFEST.json.
+
+    adam.py:  _create_slots: non-slot variables beta1_power = beta1, beta2_power = beta2; slots m, v = 0
+              _prepare:      lr, beta1, beta2, epsilon -> tensors (cast to the variable dtype at use)
+              _apply_dense:  training_ops.apply_adam(var, m, v, beta1_power, beta2_power, lr, beta1, beta2, eps, grad)
+              _finish:       after all updates: beta1_power *= beta1; beta2_power *= beta2
+    training_ops.cc (ApplyAdam functor, T = float):
+              alpha = lr * sqrt(T(1) - beta2_power) / (T(1) - beta1_power)
+              m += (grad - m) * (T(1) - beta1)
+              v += (grad.square() - v) * (T(1) - beta2)
+              var -= (m * alpha) / (v.sqrt() + epsilon)
+    apply_gradients(..., global_step=None) leaves the step counter alone (02:61 relies on it)."""
+
+    def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-8, use_locking=False, name="Adam"):
+        Optimizer.__init__(self, use_locking, name)
+        self._lr, self._beta1, self._beta2, self._epsilon = learning_rate, beta1, beta2, epsilon
+        self._slots = {}
+        self._beta1_power = self._beta2_power = None
+
+    def get_slot(self, var, name):
+        return self._slots[(id(var), name)]
+
+    def _get_beta_accumulators(self):
+        return self._beta1_power, self._beta2_power
+
+    def apply_gradients(self, grads_and_vars, global_step=None, name=None):
+        pairs = [(g, v) for g, v in grads_and_vars if g is not None]      # optimizer.py: vars with no grad are skipped
+        if not pairs:
+            raise ValueError("No gradients provided for any variable")
+        if self._beta1_power is None:
+            self._beta1_power = Variable(np.float32(self._beta1), trainable=False, name=f"{self._name}/beta1_power", dtype=float32)
+            self._beta2_power = Variable(np.float32(self._beta2), trainable=False, name=f"{self._name}/beta2_power", dtype=float32)
+        f32 = np.float32
+        lr_t = convert_to_tensor(self._lr, float32) if not isinstance(self._lr, Tensor) else self._lr
+        b1, b2, eps = f32(self._beta1), f32(self._beta2), f32(self._epsilon)
+        b1p, b2p = self._beta1_power, self._beta2_power
+        updates = []
+        for g, var in pairs:
+            base = var.name.split(":")[0]
+            for sl in ("m", "v"):
+                if (id(var), sl) not in self._slots:
+                    self._slots[(id(var), sl)] = Variable(np.zeros(var.value.shape, np.float32), trainable=False,
+                                                          name=f"{base}/{self._name}" + ("" if sl == "m" else "_1"), dtype=float32)
+            m, v = self._slots[(id(var), "m")], self._slots[(id(var), "v")]
+
+            def fn(r, grad, lr, _var=var, _m=m, _v=v):
+                grad = np.asarray(grad, dtype=f32)
+                one = f32(1.0)
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    alpha = f32(f32(f32(lr) * np.sqrt(f32(one - f32(b2p.value)))) / f32(one - f32(b1p.value)))
+                    _m.value = np.add(_m.value, np.multiply(np.subtract(grad, _m.value, dtype=f32), f32(one - b1), dtype=f32), dtype=f32)
+                    _v.value = np.add(_v.value, np.multiply(np.subtract(np.multiply(grad, grad, dtype=f32), _v.value, dtype=f32),
+                                                            f32(one - b2), dtype=f32), dtype=f32)
+                    _var.value = np.subtract(_var.value, np.divide(np.multiply(_m.value, alpha, dtype=f32),
+                                                                   np.add(np.sqrt(_v.value, dtype=f32), eps, dtype=f32), dtype=f32), dtype=f32)
+                return None
+            updates.append(Tensor(fn, [convert_to_tensor(g, float32), lr_t], None, (), "ApplyAdam"))
+        with control_dependencies(updates):                        # _finish
+            up1 = b1p.assign(b1p * b1)
+            up2 = b2p.assign(b2p * b2)
+        ops = updates + [up1, up2]
+        if global_step is not None:
+            with control_dependencies(ops):
+                ops = ops + [global_step.assign_add(1)]
+        return group(*ops, name=name or self._name)
+
+
+def assign_add(ref, value, use_locking=None, name=None):
+    return ref.assign_add(value)
+
+
 def _get_or_create_global_step():
     if _g.global_step is None:
         _g.global_step = Variable(np.int64(0), trainable=False, name="global_step", dtype=int64)
@@ -400,10 +476,12 @@ def _get_or_create_global_step():
 
 train = types.SimpleNamespace(
     Optimizer=Optimizer,
+    AdamOptimizer=AdamOptimizer,
     polynomial_decay=_polynomial_decay,
     get_or_create_global_step=_get_or_create_global_step,
     get_global_step=lambda: _g.global_step,
 )
+compat = types.SimpleNamespace(v1=types.SimpleNamespace(train=train))
 math = types.SimpleNamespace(
     equal=lambda x, y, name=None: _binary(np.equal, x, y, "Equal", out_dtype=bool_),
 )

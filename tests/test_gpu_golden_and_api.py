@@ -36,6 +36,45 @@ def test_cuda_path_reproduces_reference_fixtures(case):
         assert exact                           # the whole trajectory was bit-identical
 
 
+def test_cuda_path_reproduces_recipe_fixtures():
+    """Variant B (a14) against the AST-lifted recipes of 02 / 04 / another-example executed over the stub:
+    tf.train.AdamOptimizer inside the accumulation window, N from params, no clip.  No reduction is involved
+    (no global norm), every op is one correctly rounded fp32 op: the CUDA path must be bit-identical."""
+    import gaccum_b200 as g
+    from gaccum_b200.train_op import GaccumTrainOp
+    from golden_util import RecipeGolden, recipe_cases
+    assert len(recipe_cases()) >= 4
+    for case in recipe_cases():
+        gd = RecipeGolden(case)
+        tp = [torch.from_numpy(p).cuda() for p in gd.init()]
+        op = GaccumTrainOp(tp, gd.names, g.HParams.tf_adam(), gd.N, lambda s, _lr=gd.lr: _lr)
+        for s in range(gd.steps):
+            applied = op.run([torch.from_numpy(x).cuda() for x in gd.grads(s)])
+            assert applied == (s % gd.N == 0) and op.global_step == int(gd.z[f"global_step/{s}"])
+            if s in gd.recorded:
+                for i, n in enumerate(gd.names):
+                    gd.check(f"param/{s}/{n}", tp[i].cpu().numpy()); gd.check(f"accum/{s}/{n}", op.accum_view(i).cpu().numpy())
+                    gd.check(f"m/{s}/{n}", op.m_view(i).cpu().numpy()); gd.check(f"v/{s}/{n}", op.v_view(i).cpu().numpy())
+                assert np.float32(op.beta1_power) == gd.z[f"beta1_power/{s}"] and np.float32(op.beta2_power) == gd.z[f"beta2_power/{s}"]
+
+
+def test_direct_apply_gradients_skips_none_pairs_like_the_reference():
+    """optimization.AdamWeightDecayOptimizer(...).apply_gradients(zip(grads, tvars)) with one grad None:
+    the reference skips the pair (optimization.py:132-133): no slots, no weight decay, parameter untouched."""
+    from gaccum_b200 import graph, optimization as opt
+    from golden_util import DirectApplyGolden
+    gd = DirectApplyGolden()
+    graph.reset_default_graph()
+    tvars = [graph.add_variable(n, torch.from_numpy(gd.z[f"init/{n}"].copy()).cuda()) for n in gd.names]
+    optimizer = opt.AdamWeightDecayOptimizer(learning_rate=gd.lr, weight_decay_rate=0.01, beta_1=0.9, beta_2=0.999, epsilon=1e-6,
+                                             exclude_from_weight_decay=["LayerNorm", "layer_norm", "bias"])
+    for s in range(gd.steps):
+        grads = [None if i == gd.none_at else torch.from_numpy(gd.z[f"grad/{s}/{n}"]).cuda() for i, n in enumerate(gd.names)]
+        optimizer.apply_gradients(zip(grads, tvars))
+        for i, n in enumerate(gd.names):
+            assert np.array_equal(tvars[i].tensor.cpu().numpy(), gd.z[f"param/{s}/{n}"]), f"step {s} {n}"
+
+
 def _tiny_model():
     torch.manual_seed(0)
     m = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.LayerNorm(32), torch.nn.Tanh(), torch.nn.Linear(32, 2)).cuda()

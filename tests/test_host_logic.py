@@ -21,7 +21,7 @@ def test_header_symbols_are_exported():
     lib = ctypes.CDLL(g.lib_path())
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, f"declared in gaccum.h but not exported: {missing}"
-    assert g.version() == 100
+    assert g.version() == 200
 
 
 def test_library_has_no_torch_or_oracle_dependency():

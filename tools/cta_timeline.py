@@ -1,8 +1,11 @@
 #!/usr/bin/env python
-"""Per-CTA timeline of the clip-apply kernel (GACCUM_EXPERIMENTS=1): where does each CTA wait?"""
+"""Per-CTA timeline of the clip-apply kernel: where does each CTA wait?  Needs the experiments build
+(python gradient-accumulation-tf-estimator_b200/build.py --variant exp GACCUM_EXPERIMENTS), which this
+script selects through GACCUM_LIB; the shipped libgaccum.so carries no timestamp code."""
 import ctypes as C, os, sys
-os.environ["GACCUM_EXPERIMENTS"] = "1"
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+os.environ.setdefault("GACCUM_LIB", os.path.join(ROOT, "gradient-accumulation-tf-estimator_b200", "csrc", "libgaccum_exp.so"))
+sys.path.insert(0, ROOT)
 import numpy as np, torch
 import gaccum_b200 as g
 from gaccum_b200.manifests import MANIFESTS
@@ -23,9 +26,11 @@ for it in range(12):
         op.run_bound(b)
 torch.cuda.synchronize()
 op = sets[0][0]
-buf = (C.c_ulonglong * (4 * 148))()
-assert L.gaccum_debug_read(op.plan._h, buf, 4 * 148) == 0
-t = np.array(buf, dtype=np.float64).reshape(148, 4)
+buf = (C.c_ulonglong * (16 * 148))()
+assert L.gaccum_debug_read(op.plan._h, buf, 16 * 148) == 0
+raw = np.array(buf, dtype=np.float64).reshape(148, 16)
+t = raw[:, :4].copy()
+cyc = raw[:, 4:16] / 1.965e3       # cycles -> us at 1965 MHz
 t0 = t[:, 0].min()
 t = (t - t0) / 1e3
 for name, col in (("start", 0), ("pass1 done", 1), ("barrier out", 2), ("pass2 done", 3)):
@@ -34,3 +39,6 @@ for name, col in (("start", 0), ("pass1 done", 1), ("barrier out", 2), ("pass2 d
 p1 = t[:, 1] - t[:, 0]; p2 = t[:, 3] - t[:, 2]
 print(f"pass1 duration per CTA: min {p1.min():.1f} median {np.median(p1):.1f} max {p1.max():.1f}; waiting at barrier: mean {np.mean(t[:,2]-t[:,1]):.1f} us")
 print(f"pass2 duration per CTA: min {p2.min():.1f} median {np.median(p2):.1f} max {p2.max():.1f}; idle before kernel end: mean {np.mean(t[:,3].max()-t[:,3]):.1f} us")
+for name, lo in (("consumers waiting for G (per group)", 0), ("producer waiting for a free slot", 3), ("group pass-1 duration", 6), ("producer: all copies issued after", 9)):
+    c = cyc[:, lo:lo + 3]
+    print(f"{name:36s} min {c.min():6.1f}  median {np.median(c):6.1f}  max {c.max():6.1f} us")
