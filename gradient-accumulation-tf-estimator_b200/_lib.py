@@ -152,7 +152,28 @@ def _c_strs(strs: Sequence[str]):
 
 def decay_mask(names: Sequence[str], weight_decay_rate: float,
                exclude: Optional[Sequence[str]] = ("LayerNorm", "layer_norm", "bias")) -> List[bool]:
-    """optimization.py:179-194."""
+    """optimization.py:179-194, with the reference's own regular-expression engine: Python ``re.search`` on the
+    name with a trailing ``:<digits>`` stripped.  (The C helper ``gaccum_decay_mask`` is for non-Python callers and
+    speaks POSIX ERE: identical for the reference's plain substrings, different for Python-only syntax such as
+    ``\\d`` or look-arounds -- both Python bindings therefore evaluate the patterns here.)"""
+    import re
+    out = []
+    for n in names:
+        m = re.match("^(.*):\\d+$", n)                      # _get_variable_name, optimization.py:189-194
+        if m is not None:
+            n = m.group(1)
+        use = bool(weight_decay_rate)                       # :181
+        if use and exclude:
+            for r in exclude:
+                if re.search(r, n) is not None:             # :183-186
+                    use = False
+        out.append(use)
+    return out
+
+
+def decay_mask_c(names: Sequence[str], weight_decay_rate: float,
+                 exclude: Optional[Sequence[str]] = ("LayerNorm", "layer_norm", "bias")) -> List[bool]:
+    """The C ABI's ``gaccum_decay_mask`` (POSIX extended regular expressions)."""
     exclude = list(exclude or [])
     out = (C.c_uint8 * len(names))()
     n, e = _c_strs(names), _c_strs(exclude)

@@ -61,6 +61,8 @@ struct gaccum_plan {
   double* d_partials = nullptr;
   float* d_stats = nullptr;
   uint32_t* d_dp_sync = nullptr;           // data-parallel kernel: block-completion counters (zero between launches)
+  unsigned long long* d_barrier = nullptr; // clip-apply kernel: monotonic arrival counter of the consumers' grid barrier
+  int tmem_tiles = kTmemTiles;             // tiles of a' per consumer group parked in Tensor Memory (GACCUM_TMEM_TILES: A/B)
 #ifdef GACCUM_EXPERIMENTS
   unsigned long long* d_debug = nullptr;   // per-CTA timestamps (tools/cta_timeline.py; experiments build only)
 #endif
@@ -69,8 +71,7 @@ struct gaccum_plan {
   uint32_t flags = 0;  // kFlag* bits; GACCUM_FLAGS selects A/B measurement variants (all compute the same result)
   std::mutex mu;
   std::map<const void*, int> grid_cache;   // kernel -> co-resident grid size
-  std::map<const void*, int> stash_cache;  // kernel -> shared-memory stash tiles per consumer group
-  int smem_per_sm = 0, smem_optin = 0, stash_override = -1;
+  int smem_per_sm = 0, smem_optin = 0;
 };
 
 static int build_layout(gaccum_plan* pl) {
@@ -169,41 +170,27 @@ static int launch_apply_noclip(gaccum_plan* pl, KernelParams<CAP>& prm, cudaStre
   return GACCUM_OK;
 }
 
-// clip-apply: one cooperative launch, ONE 864-thread CTA per SM (it allocates all of Tensor Memory and most of
-// shared memory, so a second CTA could never be co-resident -- the grid is clamped to the SM count, not
-// derived from the occupancy API)
+// clip-apply: one cooperative launch, ONE 864-thread CTA per SM (it allocates all of Tensor Memory, so a second
+// CTA could never be co-resident -- the grid is clamped to the SM count, not derived from the occupancy API)
 template <int VARIANT, bool HAS_G, int CAP>
 static int launch_apply_clip(gaccum_plan* pl, KernelParams<CAP>& prm, cudaStream_t st) {
   const void* fn = (const void*)&apply_clip_kernel<VARIANT, HAS_G, CAP>;
-  int slots = 0;
   {
     std::lock_guard<std::mutex> lk(pl->mu);
-    auto it = pl->stash_cache.find(fn);
-    if (it == pl->stash_cache.end()) {
-      cudaFuncAttributes fa{};
-      CUDA_TRY(cudaFuncGetAttributes(&fa, fn));
-      const int group_bytes = kSlotVecs * 16 * kGroups;          // one slot for each of the three groups
-      // kMaxSlots x 3 x 8 KB = 192 KB is the largest pool that fits the 196 KB shared-memory carve-out: one step
-      // more and L1 drops from 60 KB to 28 KB, which starves pass 2's in-flight loads (measured, r02_tune_sweep.md)
-      int s_tiles = std::min(kMaxSlots, (pl->smem_optin - (int)fa.sharedSizeBytes) / group_bytes);
-      if (pl->stash_override > 0) s_tiles = std::min(s_tiles, pl->stash_override);
-      if (s_tiles < 1) return fail(GACCUM_ECUDA, "apply_clip_kernel: no room for one tile slot per group in shared memory");
-      const int dyn = s_tiles * group_bytes;
-      CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    if (pl->grid_cache.find(fn) == pl->grid_cache.end()) {
+      CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes));
       int per_sm = 0;
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kClipThreads, (size_t)dyn));
-      if (per_sm < 1) return fail(GACCUM_ECUDA, "apply_clip_kernel does not fit on an SM (%d B dynamic shared memory)", dyn);
-      pl->stash_cache[fn] = s_tiles;
-      it = pl->stash_cache.find(fn);
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kClipThreads, (size_t)kRingBytes));
+      if (per_sm < 1) return fail(GACCUM_ECUDA, "apply_clip_kernel does not fit on an SM (%d B dynamic shared memory)", kRingBytes);
+      pl->grid_cache[fn] = pl->num_sms;
     }
-    slots = it->second;
   }
-  const int grid = std::max(1, std::min(pl->num_sms, (prm.num_tiles + kGroups - 1) / kGroups));
-  prm.stash_tiles = slots;
-  prm.tmem_tiles = kTmemTiles;
-  const size_t smem = (size_t)slots * kSlotVecs * 16 * kGroups;
+  // the grid must be the same for every launch on this plan: the consumers' barrier counter advances by gridDim.x
+  const int grid = std::max(1, std::min(pl->num_sms, ((int)pl->tiles.size() + kGroups - 1) / kGroups));
+  prm.barrier = pl->d_barrier;
+  prm.tmem_tiles = pl->tmem_tiles;
   void* args[] = {(void*)&prm};
-  CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kClipThreads), args, smem, st));
+  CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kClipThreads), args, (size_t)kRingBytes, st));
   return GACCUM_OK;
 }
 
@@ -307,7 +294,7 @@ static int check_args(const gaccum_step_args* a) {
 }
 
 static void free_plan_device(gaccum_plan* pl) {
-  cudaFree(pl->d_tiles); cudaFree(pl->d_partials); cudaFree(pl->d_stats); cudaFree(pl->d_dp_sync);
+  cudaFree(pl->d_tiles); cudaFree(pl->d_partials); cudaFree(pl->d_stats); cudaFree(pl->d_dp_sync); cudaFree(pl->d_barrier);
 #ifdef GACCUM_EXPERIMENTS
   cudaFree(pl->d_debug);
 #endif
@@ -404,9 +391,9 @@ int gaccum_plan_create(gaccum_plan** out, int32_t T, const int64_t* numels, cons
   if (hp->variant == GACCUM_ADAM_WEIGHT_DECAY && decay) pl->decay.assign(decay, decay + T);
   if (int rc = build_layout(pl)) { delete pl; return rc; }
   pl->device = -1;
-  // GACCUM_FLAGS: A/B measurement variants of the clip-apply kernel (kFlag* in gaccum_kernels.cuh); every
-  // combination computes the same result.  Timing experiments that change results do not exist in this build.
-  if (const char* t = getenv("GACCUM_FLAGS")) pl->flags = (uint32_t)strtoul(t, nullptr, 0) & (kFlagNoL2Prefetch | kFlagNoCrossPrefetch);
+  // GACCUM_TMEM_TILES: A/B measurement knob of the clip-apply kernel (how many a' tiles per group are parked in
+  // Tensor Memory); every value computes the same result.  Result-changing timing experiments do not exist in this build.
+  if (const char* t = getenv("GACCUM_TMEM_TILES")) pl->tmem_tiles = std::max(0, std::min(kTmemTiles, atoi(t)));
   if (device >= 0) {
     int n = gaccum_device_count();
     if (device >= n) { delete pl; return fail(GACCUM_ENODEVICE, "CUDA device %d requested but %d device(s) visible; libgaccum has no CPU fallback", device, n); }
@@ -418,7 +405,6 @@ int gaccum_plan_create(gaccum_plan** out, int32_t T, const int64_t* numels, cons
     pl->num_sms = prop.multiProcessorCount;
     pl->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
     pl->smem_optin = (int)prop.sharedMemPerBlockOptin;
-    if (const char* t = getenv("GACCUM_STASH_TILES")) pl->stash_override = atoi(t);
     pl->max_grid = pl->num_sms * 16;
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_tiles, tb);
     if (e == cudaSuccess && !pl->tiles.empty())
@@ -426,6 +412,8 @@ int gaccum_plan_create(gaccum_plan** out, int32_t T, const int64_t* numels, cons
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_partials, sizeof(double) * (size_t)pl->max_grid);
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_dp_sync, sizeof(uint32_t) * 8);
     if (e == cudaSuccess) e = cudaMemset(pl->d_dp_sync, 0, sizeof(uint32_t) * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_barrier, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(pl->d_barrier, 0, sizeof(unsigned long long));
 #ifdef GACCUM_EXPERIMENTS
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_debug, sizeof(unsigned long long) * 16 * (size_t)pl->max_grid);
     if (e == cudaSuccess) e = cudaMemset(pl->d_debug, 0, sizeof(unsigned long long) * 16 * (size_t)pl->max_grid);

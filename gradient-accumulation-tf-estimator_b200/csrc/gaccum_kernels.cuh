@@ -88,8 +88,8 @@ struct KernelParams {
   double* partials;   // one per CTA (apply with clip)
   float* stats;       // gaccum_stats
   uint32_t flags;     // kFlag* bits (all of them produce correct results)
-  int32_t stash_tiles;  // apply_clip_kernel: tiles of a' each consumer group keeps in shared memory between the passes
-  int32_t tmem_tiles;   // ... and in Tensor Memory (0 or kTmemTiles)
+  unsigned long long* barrier;  // apply_clip_kernel: monotonic arrival counter of the consumers' grid barrier
+  int32_t tmem_tiles;   // apply_clip_kernel: tiles of a' each consumer group parks in Tensor Memory (0..kTmemTiles)
 #ifdef GACCUM_EXPERIMENTS
   unsigned long long* debug;  // 16 words per CTA: 4 timestamps (ns) + wait-cycle counters (tools/cta_timeline.py)
 #endif
@@ -98,8 +98,6 @@ struct KernelParams {
 };
 
 constexpr uint32_t kFlagAssign = 1u;        // accumulate_kernel stores G instead of adding it (host-session gather of small tensors)
-constexpr uint32_t kFlagNoL2Prefetch = 2u;  // apply_clip_kernel: producer does not run bulk L2 prefetches ahead (A/B measurement)
-constexpr uint32_t kFlagNoCrossPrefetch = 4u;  // apply_clip_kernel: no L2 prefetch of pass 2's first p/m/v tiles before the barrier
 
 // ---------------------------------------------------------------------------------------------
 // memory helpers: G is read exactly once -> streaming (evict-first) loads; zeroing the
@@ -359,43 +357,28 @@ __device__ __forceinline__ double block_reduce_to_double(double x, double* smem 
 // Every consumer group behaves like an independent 256-thread CTA with virtual block id
 // b = blockIdx * 3 + group and owns tiles b, b + 3*grid, b + 6*grid, ...  (its sequence j = 0..C-1).
 //
-// Pass 1 is latency-bound when the consumers issue all of their own loads: an LDG-fed loop can keep only
-// as many bytes in flight as it has registers to land them in, and it stalls once per iteration on a
-// dependent descriptor load (measured in round 1: 4.6 TB/s, two tiles = 32 registers per thread in
-// flight).  Shared memory that a TMA ring would need is the same shared memory the a' stash needs (L2 can
-// hold only ~50 MB of a' across the two passes, and above 196 KB of shared memory the SM's L1 shrinks to
-// 28 KB, which starves pass 2) -- so here THE RING IS THE STASH:
-//   * each group has M tile slots (8 KB).  Its producer warp fetches tile descriptors 32 at a time (one per
-//     lane, shuffled out) and streams the GRADIENT tile j into slot j % M with one TMA bulk copy
-//     (cp.async.bulk shared <- global, completing on the slot's `full` mbarrier by byte count), as soon as
-//     the consumers have released the slot (`empty` mbarrier, one arrive per warp).  Up to M x 8 KB of G
-//     per group are in flight, no registers involved;
-//   * the consumers load the ACCUMULATOR tile themselves, two tiles ahead (16 registers), helped by a
-//     bulk L2 prefetch the producer issues a few tiles ahead; they wait on `full`, read G out of the slot
-//     (thread t reads word t: conflict free), a' = a + G, reduce sum((a'/N)^2);
-//   * where a' goes depends on j: the first n_tm tiles -> Tensor Memory; the middle ones -> back in place
-//     in global memory tagged L2::evict_last; the LAST M tiles -> IN PLACE OVER G IN THEIR SLOT, which is
-//     never recycled again: at the end of pass 1 the ring has become the stash, no byte of shared memory
-//     was ever only a staging buffer.
-// The producers never wait for the grid barrier: when their last copy is issued they prefetch the first
-// p/m/v tile of pass 2 into L2, so HBM keeps streaming while the CTAs rendezvous.
-// Pass 2 takes the L2-resident tiles first, youngest first, then the slots, then Tensor Memory.  Thread t of
-// a group reads back exactly the words it wrote, so neither stash needs synchronisation.
-//
-// Tiles whose gradient pointer is not 16-byte aligned (views into a flat buffer) or that are shorter than
-// one float4 cannot be moved by bulk copies: producer and consumers evaluate the same predicate
-// (bulk_vecs); for such tiles the producer only completes the slot's barrier and the consumers load the
-// tile with scalar LDGs.  Every tile goes through the same full/empty protocol, so phases never skew.
+// NO consumer ever issues a bulk load: every input stream of both passes is moved by TMA
+// (cp.async.bulk shared <- global, completing on an mbarrier by byte count) into a per-group ring in
+// shared memory, fed by the group's producer warp.  Why (measured, profiles/r02_tune_sweep.md):
+//   * an LDG-fed pass can keep only as many bytes in flight as it has registers AND L1 lines to land them
+//     in; L1 and shared memory split 256 KB, so every KB of on-chip stash was paid for with bytes in
+//     flight (round 1: pass 1 at 4.6 TB/s with 192 KB of stash and 60 KB of L1);
+//   * TMA loads need neither registers nor L1: bytes in flight = ring size, descriptors and addresses are
+//     computed by one lane per group far ahead of the consumers, and the consumers' loop is
+//     wait -> LDS -> math -> store.
+// pass 1   ring slot = [G tile | a tile] (16 KB, kP1Slots per group).  a' = a + G, reduce sum((a'/N)^2)
+//          (thread fp32 per tile -> fp64 running sum -> warp shuffle -> shared memory -> one fp64 partial
+//          per CTA).  a' of the group's first kTmemTiles tiles is parked in Tensor Memory (tcgen05.st: 256 KB
+//          per SM that a kernel without MMA leaves idle), the rest goes back in place tagged L2::evict_last.
+// barrier  only the CONSUMERS rendezvous (named barrier + one atomic per CTA).  The producers do not: p, m, v do
+//          not depend on the clip scale, so as soon as pass 1 is issued and its slots are drained they start
+//          streaming pass 2's tiles into the ring -- HBM stays busy while the CTAs wait for each other.
+// pass 2   ring slot = [p | m | v] (24 KB, kP2Slots per group); L2-resident tiles youngest first, then the
+//          Tensor-Memory tiles: clip, AdamWeightDecay/Adam, STG p, m, v, a = 0.
+// Tiles that bulk copies cannot move (gradient / parameter pointer not 16-byte aligned, or shorter than one
+// float4) go through the same full/empty protocol with nothing copied and are loaded by the consumers with
+// scalar LDGs; producer and consumers evaluate the same predicates (bulk_vecs / aligned16(p)).
 // =============================================================================================
-// ---------------------------------------------------------------------------------------------
-// Tensor Memory as a scratchpad.  TMEM (256 KB per SM, 512 columns x 128 lanes x 32 bit) normally
-// holds tcgen05.mma accumulators; this kernel has no MMA, so it is idle silicon -- 37 MB across the
-// chip, more than the shared-memory stash.  The CTA allocates all 512 columns (one CTA per SM by
-// construction); every consumer warp parks a' values in the 32 lanes it may address
-// (lane quadrant = warp % 4; the 6 warps sharing a quadrant take 80 columns each):
-// tcgen05.st 32x32b.x8 writes the thread's 8 words of a tile to 8 consecutive columns of its own
-// lane, tcgen05.ld reads them back in pass 2.  A thread only ever reads what it wrote itself.
-// ---------------------------------------------------------------------------------------------
 constexpr int kGroups = 3;                        // consumer groups per CTA
 constexpr int kConsumerThreads = kThreads * kGroups;        // 768
 constexpr int kClipThreads = kConsumerThreads + 32 * kGroups;   // + one producer warp per group = 864
@@ -403,16 +386,17 @@ constexpr int kTmemCols = 512;                    // one CTA per SM: take all co
 constexpr int kTmemColsPerWarp = 80;              // 6 warps share a lane quadrant: 6 x 80 = 480 <= 512
 constexpr int kTmemTiles = kTmemColsPerWarp / 8;  // 10 tiles per group
 constexpr uint32_t kNoTmem = 0xffffffffu;
-constexpr int kMaxSlots = 8;                      // tile slots per group (3 x 8 x 8 KB = 192 KB: the largest pool that keeps L1 at 60 KB)
-#ifdef GACCUM_A_VIA_TMA                           // measurement variant: the accumulator tile travels by TMA too (slot = G | a)
-constexpr int kSlotVecs = 2 * (kTile / 4);
-#else
-constexpr int kSlotVecs = kTile / 4;
+#ifndef GACCUM_P1_SLOTS
+#define GACCUM_P1_SLOTS 3
 #endif
-#ifndef GACCUM_A_PREFETCH_TILES
-#define GACCUM_A_PREFETCH_TILES 3
-#endif
-constexpr int kAPrefetch = GACCUM_A_PREFETCH_TILES;   // bulk L2 prefetch distance for the accumulator stream, in tiles per group
+constexpr int kP1Slots = GACCUM_P1_SLOTS;         // pass-1 ring slots per group, 16 KB each
+constexpr int kP1SlotVecs = 2 * (kTile / 4);      // float4 per pass-1 slot: G | a
+constexpr int kP2SlotVecs = 3 * (kTile / 4);      // float4 per pass-2 slot: p | m | v
+constexpr int kRingVecs = kP1Slots * kP1SlotVecs; // per group
+constexpr int kP2Slots = kRingVecs / kP2SlotVecs; // 3 x 16 KB = 48 KB -> 2 x 24 KB
+constexpr int kRingBytes = kGroups * kRingVecs * 16;   // dynamic shared memory of the kernel (144 KB)
+static_assert(kP2Slots >= 1 && kP1Slots <= 8, "ring must hold at least one [p|m|v] slot");
+constexpr int kMaxSlots = 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -438,10 +422,24 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
-__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor Memory as a scratchpad.  TMEM (256 KB per SM, 512 columns x 128 lanes x 32 bit) normally
+// holds tcgen05.mma accumulators; this kernel has no MMA, so it is idle silicon -- 37 MB across the
+// chip.  The CTA allocates all 512 columns (one CTA per SM by construction); every consumer warp parks
+// a' values in the 32 lanes it may address (lane quadrant = warp % 4; the 6 warps sharing a quadrant
+// take 80 columns each): tcgen05.st 32x32b.x8 writes the thread's 8 words of a tile to 8 consecutive
+// columns of its own lane, tcgen05.ld reads them back in pass 2.  A thread only ever reads what it
+// wrote itself.
+// ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"((uint32_t)kTmemCols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -471,60 +469,36 @@ __device__ __forceinline__ uint32_t tmem_slot_addr(uint32_t base, int slot) {
   return base + (((warp & 3u) * 32u) << 16) + (warp >> 2) * kTmemColsPerWarp + (uint32_t)slot * 8u;
 }
 
-// Number of float4 vectors of this tile that take the vector path (0: scalar fallback).  The producer and
+// Number of float4 vectors of this tile that pass 1 moves by bulk copy (0: scalar fallback).  The producer and
 // the consumers MUST agree on this.
 __device__ __forceinline__ uint32_t bulk_vecs(const TileDesc& d, const float* g) {
   return (g == nullptr || aligned16(g)) ? (d.len >> 2) : 0u;
 }
+// ... and that pass 2 moves by bulk copy
+__device__ __forceinline__ uint32_t bulk_vecs2(const TileDesc& d, const float* p) {
+  return aligned16(p) ? (d.len >> 2) : 0u;
+}
 
-// a tile may be stashed on chip only if BOTH passes will take the vector path for it
+// a' of a tile may be parked in Tensor Memory only if BOTH passes take the vector path for it and it is a full tile
 template <bool HAS_G, int CAP>
-__device__ __forceinline__ bool stashable(const TileDesc& d, const KernelParams<CAP>& prm) {
-  bool ok = aligned16(param_ptr(prm.tab, d));
+__device__ __forceinline__ bool tmem_ok(const TileDesc& d, const KernelParams<CAP>& prm) {
+  bool ok = d.len == (uint32_t)kTile && aligned16(param_ptr(prm.tab, d));
   if constexpr (HAS_G) { const float* g = grad_ptr(prm.tab, d); ok = ok && (g == nullptr || aligned16(g)); }
   return ok;
 }
 
-// how a group's C tiles are split between Tensor Memory, L2 and the slots
-struct TileClasses {
-  int count;      // C
-  int first_st;   // tiles j >= first_st stay in slot j % M
-  int n_tm;       // tiles j < n_tm go to Tensor Memory
+// one producer lane's view of a ring: slot index + how often the ring has wrapped
+struct RingPos {
+  int slot = 0;
+  uint32_t use = 0;
+  __device__ __forceinline__ void advance(int nslots) { if (++slot == nslots) { slot = 0; ++use; } }
 };
-__device__ __forceinline__ TileClasses classify(int count, int slots, int tmem_tiles) {
-  TileClasses c;
-  c.count = count;
-  c.first_st = count - min(slots, count);
-  c.n_tm = min(tmem_tiles, c.first_st);
-  return c;
-}
 
-struct ARegs { float4 v[kUnroll]; };
-
-// ---- pass 1, consumer side: issue the accumulator loads of one tile (consumed two tiles later) ----
+// ---- pass 1, consumer side: one tile out of slot [G | a] -------------------------------------------------
 template <bool HAS_G, int CAP>
-__device__ __forceinline__ void norm_issue_a(const TileDesc& d, const KernelParams<CAP>& prm, const bool to_l2,
-                                             const uint64_t pol, ARegs& r) {
-  const float* g = nullptr;
-  if constexpr (HAS_G) g = grad_ptr(prm.tab, d);
-  const uint32_t nvec = bulk_vecs(d, g), tid = threadIdx.x & (kThreads - 1);
-  const float4* a4 = reinterpret_cast<const float4*>(prm.accum + (size_t)d.soff32 * kSlabAlign);
-#ifndef GACCUM_A_VIA_TMA
-#pragma unroll
-  for (int u = 0; u < kUnroll; ++u) {
-    const uint32_t i = u * kThreads + tid;
-    if (i < nvec) r.v[u] = to_l2 ? ld_policy(a4 + i, pol) : __ldcs(a4 + i);   // the line a' returns to keeps evict_last
-  }
-#endif
-}
-
-// ---- pass 1, consumer side: finish one tile.  slot: this tile's slot (G lands there); in_slot: a' stays in it ----
-// release: ring phase, the slot is handed back to the producer once G is in registers
-template <bool HAS_G, int CAP>
-__device__ __forceinline__ float norm_finish(const TileDesc& d, const KernelParams<CAP>& prm, ARegs& r, float4* slot,
-                                             uint64_t* full, uint64_t* empty, const uint32_t parity, const bool release,
-                                             const bool in_slot, const uint32_t tmem, const uint64_t pol,
-                                             long long& dbg_wait /* experiments build: cycles spent waiting for G */) {
+__device__ __forceinline__ float norm_tile(const TileDesc& d, const KernelParams<CAP>& prm, const float4* slot,
+                                           uint64_t* full, uint64_t* empty, const uint32_t parity,
+                                           const uint32_t tmem, const uint64_t pol, long long& dbg_wait) {
   const float* __restrict__ g = nullptr;
   if constexpr (HAS_G) g = grad_ptr(prm.tab, d);
   float* __restrict__ a = prm.accum + (size_t)d.soff32 * kSlabAlign;
@@ -535,49 +509,35 @@ __device__ __forceinline__ float norm_finish(const TileDesc& d, const KernelPara
 #ifdef GACCUM_EXPERIMENTS
   const long long t_w0 = clock64();
 #endif
-  mbar_wait(full, parity);                      // G has landed (or the producer had nothing to copy)
+  mbar_wait(full, parity);                      // G and a have landed (or the producer had nothing to copy)
 #ifdef GACCUM_EXPERIMENTS
   dbg_wait += clock64() - t_w0;
 #endif
   if (nvec > 0) {
     float4* a4 = reinterpret_cast<float4*>(a);
-    float4 gg[kUnroll];
-    if (g) {
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        const uint32_t i = u * kThreads + tid;
-        if (i < nvec) gg[u] = slot[i];
-      }
-    }
-#ifdef GACCUM_A_VIA_TMA
+    float4 x[kUnroll], gg[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const uint32_t i = u * kThreads + tid;
-      if (i < nvec) r.v[u] = slot[kTile / 4 + i];
+      if (i < nvec) { x[u] = slot[kTile / 4 + i]; if (g) gg[u] = slot[i]; }
     }
-#endif
-    if (release) {                              // ring phase: hand the slot back as soon as G is in registers
-      __syncwarp();
-      if ((threadIdx.x & 31) == 0) mbar_arrive(empty);
-    }
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(empty);        // this warp is done with the slot
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const uint32_t i = u * kThreads + tid;
       if (i < nvec) {
-        float4& x = r.v[u];
         if (g) {
-          x.x = __fadd_rn(x.x, gg[u].x); x.y = __fadd_rn(x.y, gg[u].y);
-          x.z = __fadd_rn(x.z, gg[u].z); x.w = __fadd_rn(x.w, gg[u].w);
+          x[u].x = __fadd_rn(x[u].x, gg[u].x); x[u].y = __fadd_rn(x[u].y, gg[u].y);
+          x[u].z = __fadd_rn(x[u].z, gg[u].z); x[u].w = __fadd_rn(x[u].w, gg[u].w);
+          if (tmem == kNoTmem) st_policy(a4 + i, x[u], pol);
         }
-        if (in_slot) slot[i] = x;               // in place over G: the slot is now stash
-        else if (tmem != kNoTmem) {}
-        else if (g) st_policy(a4 + i, x, pol);
-        const float nx = normalize(x.x, nf, inv_nf), ny = normalize(x.y, nf, inv_nf),
-                    nz = normalize(x.z, nf, inv_nf), nw = normalize(x.w, nf, inv_nf);
+        const float nx = normalize(x[u].x, nf, inv_nf), ny = normalize(x[u].y, nf, inv_nf),
+                    nz = normalize(x[u].z, nf, inv_nf), nw = normalize(x[u].w, nf, inv_nf);
         acc = fmaf(nx, nx, acc); acc = fmaf(ny, ny, acc); acc = fmaf(nz, nz, acc); acc = fmaf(nw, nw, acc);
       }
     }
-    if (tmem != kNoTmem) tmem_store8(tmem, r.v[0], r.v[1]);   // full tile: every lane of every warp carries data
+    if (tmem != kNoTmem) tmem_store8(tmem, x[0], x[1]);   // full tile: every lane of every warp carries data
     const uint32_t i = (nvec << 2) + tid;      // < 4 tail elements always travel through global memory
     if (i < len) {
       float xs = a[i];
@@ -586,11 +546,9 @@ __device__ __forceinline__ float norm_finish(const TileDesc& d, const KernelPara
       acc = fmaf(n, n, acc);
     }
   } else {
-    // unaligned gradient view, or a tile shorter than one float4: nothing was copied, nothing is stashed
-    if (release) {
-      __syncwarp();
-      if ((threadIdx.x & 31) == 0) mbar_arrive(empty);
-    }
+    // unaligned gradient view, or a tile shorter than one float4: nothing was copied
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(empty);
     for (uint32_t i = tid; i < len; i += kThreads) {
       float xs = a[i];
       if (g) { xs = __fadd_rn(xs, ld_stream(g + i)); a[i] = xs; }
@@ -601,10 +559,10 @@ __device__ __forceinline__ float norm_finish(const TileDesc& d, const KernelPara
   return acc;
 }
 
-// ---- pass 2: one tile ------------------------------------------------------------------------------
+// ---- pass 2, consumer side: one tile out of slot [p | m | v]; a' from Tensor Memory or from L2 ----------
 template <int VARIANT, int CAP>
-__device__ __forceinline__ void update_tile2(const TileDesc d, const KernelParams<CAP>& prm, const float s,
-                                             const float4* __restrict__ stash, const uint32_t tmem) {
+__device__ __forceinline__ void update_tile2(const TileDesc& d, const KernelParams<CAP>& prm, const float s, const float4* slot,
+                                             uint64_t* full, uint64_t* empty, const uint32_t parity, const uint32_t tmem) {
   const size_t soff = (size_t)d.soff32 * kSlabAlign;
   float* __restrict__ a = prm.accum + soff;
   float* __restrict__ m = prm.m + soff;
@@ -617,23 +575,30 @@ __device__ __forceinline__ void update_tile2(const TileDesc d, const KernelParam
     const float c = __fmul_rn(normalize(ax, sc.nf, sc.inv_nf), s);     // optimization.py:83-84
     adam_elem<VARIANT>(c, px, mx, vx, decay, sc);           // :85
   };
-  if (aligned16(p)) {
-    const uint32_t nvec = len >> 2;
+  const uint32_t nvec = bulk_vecs2(d, p);
+  if (nvec > 0) {
     float4* a4 = reinterpret_cast<float4*>(a);
     float4* m4 = reinterpret_cast<float4*>(m);
     float4* v4 = reinterpret_cast<float4*>(v);
     float4* p4 = reinterpret_cast<float4*>(p);
     float4 va[kUnroll], vp[kUnroll], vm[kUnroll], vv[kUnroll];
+    if (tmem == kNoTmem) {                      // a' comes back from L2 (evict_last since pass 1): issue before waiting
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const uint32_t i = u * kThreads + tid;
+        if (i < nvec) va[u] = __ldcs(a4 + i);
+      }
+    } else {
+      tmem_load8(tmem, va[0], va[1]);
+    }
+    mbar_wait(full, parity);                    // p, m, v have landed
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const uint32_t i = u * kThreads + tid;
-      if (i < nvec) {
-        vp[u] = __ldcs(p4 + i); vm[u] = __ldcs(m4 + i); vv[u] = __ldcs(v4 + i);
-        if (stash) va[u] = stash[i];
-        else if (tmem == kNoTmem) va[u] = __ldcs(a4 + i);
-      }
+      if (i < nvec) { vp[u] = slot[i]; vm[u] = slot[kTile / 4 + i]; vv[u] = slot[2 * (kTile / 4) + i]; }
     }
-    if (tmem != kNoTmem) tmem_load8(tmem, va[0], va[1]);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(empty);
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const uint32_t i = u * kThreads + tid;
@@ -651,6 +616,9 @@ __device__ __forceinline__ void update_tile2(const TileDesc d, const KernelParam
       p[i] = px; m[i] = mx; v[i] = vx; a[i] = 0.f;
     }
   } else {
+    mbar_wait(full, parity);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(empty);
     for (uint32_t i = tid; i < len; i += kThreads) {
       float px = p[i], mx = m[i], vx = v[i];
       elem(a[i], px, mx, vx);
@@ -659,26 +627,41 @@ __device__ __forceinline__ void update_tile2(const TileDesc d, const KernelParam
   }
 }
 
-// Dynamic shared memory of apply_clip_kernel: 3 groups x slots x 8 KB tile slots.
+// Deterministic reduction over the 768 consumer threads (the producers do not take part): total in thread 0.
+__device__ __forceinline__ double consumer_reduce_to_double(double x, double* smem /* 24 */) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) smem[warp] = x;
+  named_bar_sync(1, kConsumerThreads);
+  double tot = 0.0;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < kConsumerThreads / 32; ++w) tot += smem[w];
+  return tot;
+}
+
+// Dynamic shared memory of apply_clip_kernel: 3 groups x kRingVecs float4 (144 KB).
 template <int VARIANT, bool HAS_G, int CAP>
 __global__ void __launch_bounds__(kClipThreads, 1)
 apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
   extern __shared__ __align__(128) unsigned char smem_dyn[];
-  __shared__ double red[kClipThreads / 32];
+  __shared__ double red[kConsumerThreads / 32];
   __shared__ float s_bcast[2];
   __shared__ uint32_t s_tmem_base;
-  __shared__ __align__(8) uint64_t s_full[kGroups][kMaxSlots];
-  __shared__ __align__(8) uint64_t s_empty[kGroups][kMaxSlots];
+  __shared__ __align__(8) uint64_t s_full1[kGroups][kMaxSlots], s_empty1[kGroups][kMaxSlots];
+  __shared__ __align__(8) uint64_t s_full2[kGroups][kMaxSlots], s_empty2[kGroups][kMaxSlots];
 
   const int warp = (int)threadIdx.x >> 5;
   const bool is_producer = warp >= kConsumerThreads / 32;
   const int grp = is_producer ? warp - kConsumerThreads / 32 : (int)threadIdx.x / kThreads;   // group served / group id
   const int nt = prm.num_tiles, G = (int)gridDim.x * kGroups;
-  const int M = prm.stash_tiles;                                   // slots per group (1..kMaxSlots)
   const int b = (int)blockIdx.x * kGroups + grp;                   // virtual block id
-  const TileClasses tc = classify(b < nt ? (nt - 1 - b) / G + 1 : 0, M, prm.tmem_tiles);
-  float4* const slots = reinterpret_cast<float4*>(smem_dyn) + (size_t)grp * M * kSlotVecs;
+  const int C = b < nt ? (nt - 1 - b) / G + 1 : 0;                 // tiles of this group
+  const int n_tm = min(prm.tmem_tiles, C);                         // tiles j < n_tm park a' in Tensor Memory
+  float4* const ring = reinterpret_cast<float4*>(smem_dyn) + (size_t)grp * kRingVecs;
   const uint64_t pol_last = policy_evict_last();
+  // pass 2 order: L2-resident tiles youngest first (q = 0 -> j = C-1), then the Tensor-Memory tiles
+  auto tile_of_q = [&](int q) { return q < C - n_tm ? C - 1 - q : q - (C - n_tm); };
 
 #ifdef GACCUM_EXPERIMENTS
   auto stamp = [&](int which) {
@@ -696,8 +679,10 @@ apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
   // ---- set-up: mbarriers, Tensor Memory ---------------------------------------------------------------
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int g = 0; g < kGroups; ++g)
-      for (int s = 0; s < M; ++s) { mbar_init(&s_full[g][s], 1); mbar_init(&s_empty[g][s], kThreads / 32); }
+    for (int g = 0; g < kGroups; ++g) {
+      for (int sl = 0; sl < kP1Slots; ++sl) { mbar_init(&s_full1[g][sl], 1); mbar_init(&s_empty1[g][sl], kThreads / 32); }
+      for (int sl = 0; sl < kP2Slots; ++sl) { mbar_init(&s_full2[g][sl], 1); mbar_init(&s_empty2[g][sl], kThreads / 32); }
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -707,183 +692,182 @@ apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = prm.tmem_tiles > 0 ? s_tmem_base : 0u;
 
-  double acc = 0.0;
   if (is_producer) {
     // =========================== producer warp of group `grp` ===========================
     const int lane = (int)threadIdx.x & 31;
     const uint64_t pol_first = policy_evict_first();
-    const bool l2_prefetch = !(prm.flags & kFlagNoL2Prefetch);
-    auto fetch = [&](int j0, TileDesc& d) -> bool {      // this lane's descriptor of the batch starting at j0
-      const int j = j0 + lane;
-      if (j >= tc.count) return false;
-      d = prm.tiles[b + j * G];
-      return true;
-    };
-    auto prefetch_a = [&](const TileDesc& d) {
-      const float* g = nullptr;
-      if constexpr (HAS_G) g = grad_ptr(prm.tab, d);
-      const uint32_t nv = bulk_vecs(d, g);
-      if (nv > 0) bulk_prefetch_l2(prm.accum + (size_t)d.soff32 * kSlabAlign, nv * 16u);
-    };
-    TileDesc dc, dn;
-    bool vc = fetch(0, dc), vn = fetch(32, dn);
-    if (l2_prefetch && vc && lane < kAPrefetch) prefetch_a(dc);      // the first tiles of the group
-    int slot = 0;
-    uint32_t use = 0;                                                  // how many times slot 0.. have been used: j / M
 #ifdef GACCUM_EXPERIMENTS
     long long dbg_empty = 0;
     const long long dbg_p0 = clock64();
 #endif
-    for (int j0 = 0; j0 < tc.count; j0 += 32) {
-      const int nb = min(32, tc.count - j0);
-      for (int l = 0; l < nb; ++l) {
-        TileDesc d;
-        d.tensor_flags = __shfl_sync(0xffffffffu, dc.tensor_flags, l);
-        d.len = __shfl_sync(0xffffffffu, dc.len, l);
-        d.toff = __shfl_sync(0xffffffffu, dc.toff, l);
-        d.soff32 = __shfl_sync(0xffffffffu, dc.soff32, l);
-        // accumulator stream: the lane that holds tile j + kAPrefetch pulls it into L2
-        if (l2_prefetch) {
-          const int lp = l + kAPrefetch;
-          if (lp < 32) { if (lane == lp && vc) prefetch_a(dc); }
-          else { if (lane == lp - 32 && vn) prefetch_a(dn); }
-        }
-        if (lane == 0) {
-          const float* g = nullptr;
-          if constexpr (HAS_G) g = grad_ptr(prm.tab, d);
-          const uint32_t nvec = bulk_vecs(d, g);
+    // ---- pass 1: [G | a] of tiles j = 0..C-1.  Descriptors are fetched 32 at a time, one per lane ----
+    {
+      auto fetch = [&](int j0, TileDesc& d) { const int j = j0 + lane; if (j < C) d = prm.tiles[b + j * G]; };
+      TileDesc dc{}, dn{};
+      fetch(0, dc); fetch(32, dn);
+      RingPos rp;
+      for (int j0 = 0; j0 < C; j0 += 32) {
+        const int nb = min(32, C - j0);
+        for (int l = 0; l < nb; ++l) {
+          TileDesc d;
+          d.tensor_flags = __shfl_sync(0xffffffffu, dc.tensor_flags, l);
+          d.len = __shfl_sync(0xffffffffu, dc.len, l);
+          d.toff = __shfl_sync(0xffffffffu, dc.toff, l);
+          d.soff32 = __shfl_sync(0xffffffffu, dc.soff32, l);
+          if (lane == 0) {
+            const float* g = nullptr;
+            if constexpr (HAS_G) g = grad_ptr(prm.tab, d);
+            const uint32_t nvec = bulk_vecs(d, g);
+            uint64_t* full = &s_full1[grp][rp.slot];
 #ifdef GACCUM_EXPERIMENTS
-          const long long t_e0 = clock64();
+            const long long t_e0 = clock64();
 #endif
-          mbar_wait(&s_empty[grp][slot], (use & 1u) ^ 1u);           // the consumers have released the slot
+            mbar_wait(&s_empty1[grp][rp.slot], (rp.use & 1u) ^ 1u);         // the consumers have released the slot
 #ifdef GACCUM_EXPERIMENTS
-          dbg_empty += clock64() - t_e0;
+            dbg_empty += clock64() - t_e0;
 #endif
-#ifdef GACCUM_A_VIA_TMA
-          if (nvec > 0) {
-            mbar_arrive_expect_tx(&s_full[grp][slot], nvec * 16u * (g ? 2u : 1u));
-            if (g) bulk_g2s(slots + (size_t)slot * kSlotVecs, g, nvec * 16u, &s_full[grp][slot], pol_first);
-            bulk_g2s(slots + (size_t)slot * kSlotVecs + kTile / 4, prm.accum + (size_t)d.soff32 * kSlabAlign, nvec * 16u, &s_full[grp][slot], pol_first);
-          } else {
-            mbar_arrive(&s_full[grp][slot]);
+            if (nvec > 0) {
+              float4* dst = ring + (size_t)rp.slot * kP1SlotVecs;
+              mbar_arrive_expect_tx(full, nvec * 16u * (g ? 2u : 1u));
+              if (g) bulk_g2s(dst, g, nvec * 16u, full, pol_first);
+              bulk_g2s(dst + kTile / 4, prm.accum + (size_t)d.soff32 * kSlabAlign, nvec * 16u, full, pol_first);
+            } else {
+              mbar_arrive(full);                                             // nothing to copy: complete the phase
+            }
           }
-#else
-          if (g != nullptr && nvec > 0) {
-            mbar_arrive_expect_tx(&s_full[grp][slot], nvec * 16u);
-            bulk_g2s(slots + (size_t)slot * kSlotVecs, g, nvec * 16u, &s_full[grp][slot], pol_first);
-          } else {
-            mbar_arrive(&s_full[grp][slot]);                         // nothing to copy: complete the phase
-          }
-#endif
+          rp.advance(kP1Slots);
         }
-        if (++slot == M) { slot = 0; ++use; }
+        dc = dn;
+        fetch(j0 + 64, dn);
       }
-      dc = dn; vc = vn;
-      vn = fetch(j0 + 64, dn);
+      // drain: pass 2's slots overlay pass 1's, so every pass-1 slot must have been released for the last time
+      if (lane == 0) {
+        for (int sl = 0; sl < kP1Slots; ++sl) {
+          const uint32_t n = rp.use + (sl < rp.slot ? 1u : 0u);              // times slot sl was armed
+          if (n > 0) mbar_wait(&s_empty1[grp][sl], (n - 1u) & 1u);
+        }
+      }
+      __syncwarp();
     }
 #ifdef GACCUM_EXPERIMENTS
     if (prm.debug && lane == 0) {
       prm.debug[blockIdx.x * 16 + 7 + grp] = (unsigned long long)dbg_empty;               // cycles the producer waited for a free slot
-      prm.debug[blockIdx.x * 16 + 13 + grp] = (unsigned long long)(clock64() - dbg_p0);   // cycles until the last copy was issued
+      prm.debug[blockIdx.x * 16 + 13 + grp] = (unsigned long long)(clock64() - dbg_p0);   // cycles until pass 1 was issued and drained
     }
 #endif
-    // pass 1 is fully issued: pull the first pass-2 tile's p, m, v into L2 while the CTAs rendezvous
-    if (!(prm.flags & kFlagNoCrossPrefetch) && lane == 0 && tc.count > 0) {
-      const int j = tc.first_st > tc.n_tm ? tc.first_st - 1 : tc.first_st;
-      const TileDesc d = prm.tiles[b + j * G];
-      const float* p = param_ptr(prm.tab, d);
-      const uint32_t nv = d.len >> 2;
-      if (nv > 0) {
-        const size_t soff = (size_t)d.soff32 * kSlabAlign;
-        if (aligned16(p)) bulk_prefetch_l2(p, nv * 16u);
-        bulk_prefetch_l2(prm.m + soff, nv * 16u);
-        bulk_prefetch_l2(prm.v + soff, nv * 16u);
+    // ---- pass 2: [p | m | v] in pass-2 order.  Nothing here depends on the clip scale: no grid barrier ----
+    {
+      auto fetch = [&](int q0, TileDesc& d) { const int q = q0 + lane; if (q < C) d = prm.tiles[b + tile_of_q(q) * G]; };
+      TileDesc dc{}, dn{};
+      fetch(0, dc); fetch(32, dn);
+      RingPos rp;
+      for (int q0 = 0; q0 < C; q0 += 32) {
+        const int nb = min(32, C - q0);
+        for (int l = 0; l < nb; ++l) {
+          TileDesc d;
+          d.tensor_flags = __shfl_sync(0xffffffffu, dc.tensor_flags, l);
+          d.len = __shfl_sync(0xffffffffu, dc.len, l);
+          d.toff = __shfl_sync(0xffffffffu, dc.toff, l);
+          d.soff32 = __shfl_sync(0xffffffffu, dc.soff32, l);
+          if (lane == 0) {
+            const float* p = param_ptr(prm.tab, d);
+            const uint32_t nvec = bulk_vecs2(d, p);
+            uint64_t* full = &s_full2[grp][rp.slot];
+            mbar_wait(&s_empty2[grp][rp.slot], (rp.use & 1u) ^ 1u);
+            if (nvec > 0) {
+              const size_t soff = (size_t)d.soff32 * kSlabAlign;
+              float4* dst = ring + (size_t)rp.slot * kP2SlotVecs;
+              mbar_arrive_expect_tx(full, nvec * 48u);
+              bulk_g2s(dst, p, nvec * 16u, full, pol_first);
+              bulk_g2s(dst + kTile / 4, prm.m + soff, nvec * 16u, full, pol_first);
+              bulk_g2s(dst + 2 * (kTile / 4), prm.v + soff, nvec * 16u, full, pol_first);
+            } else {
+              mbar_arrive(full);
+            }
+          }
+          rp.advance(kP2Slots);
+        }
+        dc = dn;
+        fetch(q0 + 64, dn);
       }
     }
-  } else if (tc.count > 0) {
-    // =========================== consumer group: pass 1 ===========================
-    const int C = tc.count;
-    auto desc = [&](int j) { return prm.tiles[b + j * G]; };
-    auto is_l2 = [&](int j) { return j >= tc.n_tm && j < tc.first_st; };
-    TileDesc d0 = desc(0), d1 = d0;
-    if (C > 1) d1 = desc(1);
-    ARegs r0, r1;
-    norm_issue_a<HAS_G>(d0, prm, is_l2(0), pol_last, r0);
-    if (C > 1) norm_issue_a<HAS_G>(d1, prm, is_l2(1), pol_last, r1);
-    int slot = 0;
-    uint32_t use = 0;
+    __syncwarp();
+  } else {
+    // =========================== consumer group ===========================
+    double acc = 0.0;
     long long dbg_wait = 0;
 #ifdef GACCUM_EXPERIMENTS
     const long long dbg_t0 = clock64();
 #endif
-    auto finish = [&](int j, const TileDesc& d, ARegs& r) -> float {
-      const bool in_slot = j >= tc.first_st && stashable<HAS_G>(d, prm);
-      const bool ring = j < tc.first_st;
-      uint32_t tm = kNoTmem;
-      if (j < tc.n_tm && d.len == (uint32_t)kTile && stashable<HAS_G>(d, prm)) tm = tmem_slot_addr(tmem_base, j);
-      // slots of the final M tiles are never handed back: `ring` decides the empty-arrive, `in_slot` the destination
-      const float x = norm_finish<HAS_G>(d, prm, r, slots + (size_t)slot * kSlotVecs, &s_full[grp][slot], &s_empty[grp][slot],
-                                         use & 1u, ring, in_slot, tm, pol_last, dbg_wait);
-      if (++slot == M) { slot = 0; ++use; }
-      return x;
-    };
-    for (int j = 0; j < C; j += 2) {
-      TileDesc d2 = d0, d3 = d1;
-      if (j + 2 < C) d2 = desc(j + 2);
-      if (j + 3 < C) d3 = desc(j + 3);
-      acc += (double)finish(j, d0, r0);
-      if (j + 2 < C) norm_issue_a<HAS_G>(d2, prm, is_l2(j + 2), pol_last, r0);
-      if (j + 1 < C) {
-        acc += (double)finish(j + 1, d1, r1);
-        if (j + 3 < C) norm_issue_a<HAS_G>(d3, prm, is_l2(j + 3), pol_last, r1);
+    if (C > 0) {
+      // ---- pass 1 ----
+      TileDesc d = prm.tiles[b];
+      RingPos rp;
+      for (int j = 0; j < C; ++j) {
+        TileDesc dnx = d;
+        if (j + 1 < C) dnx = prm.tiles[b + (j + 1) * G];          // next descriptor: off the critical path
+        const uint32_t tm = (j < n_tm && tmem_ok<HAS_G>(d, prm)) ? tmem_slot_addr(tmem_base, j) : kNoTmem;
+        acc += (double)norm_tile<HAS_G>(d, prm, ring + (size_t)rp.slot * kP1SlotVecs, &s_full1[grp][rp.slot], &s_empty1[grp][rp.slot],
+                                        rp.use & 1u, tm, pol_last, dbg_wait);
+        rp.advance(kP1Slots);
+        d = dnx;
       }
-      d0 = d2; d1 = d3;
     }
 #ifdef GACCUM_EXPERIMENTS
     if (prm.debug && (threadIdx.x & (kThreads - 1)) == 0) {
-      prm.debug[blockIdx.x * 16 + 4 + grp] = (unsigned long long)dbg_wait;                 // cycles waiting for G
+      prm.debug[blockIdx.x * 16 + 4 + grp] = (unsigned long long)dbg_wait;                 // cycles waiting for G | a
       prm.debug[blockIdx.x * 16 + 10 + grp] = (unsigned long long)(clock64() - dbg_t0);   // cycles of the group's pass 1
     }
 #endif
-  }
-  const double part = block_reduce_to_double(acc, red);
-  if (threadIdx.x == 0) prm.partials[blockIdx.x] = part;
-  stamp(1);
-  cg::this_grid().sync();
-  stamp(2);
-  // ---- every CTA combines the per-CTA partials in the same fixed order ---------------------------
-  if (threadIdx.x < 32) {
-    double tot = 0.0;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) tot += __ldcg(prm.partials + i);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    const double part = consumer_reduce_to_double(acc, red);
+    stamp(1);
+    // ---- grid barrier of the consumers: one atomic per CTA on a monotonic counter (every launch of this plan
+    //      uses the same grid, so the counter advances by gridDim.x per launch); cooperative launch guarantees
+    //      that all CTAs are co-resident ----
     if (threadIdx.x == 0) {
-      const float g_norm = __fsqrt_rn((float)tot);        // tf.linalg.global_norm
-      s_bcast[0] = clip_scale(g_norm, prm.sc.clip);
-      s_bcast[1] = g_norm;
+      prm.partials[blockIdx.x] = part;
+      __threadfence();
+      const unsigned long long old = atomicAdd(prm.barrier, 1ull);
+      const unsigned long long target = (old / gridDim.x + 1ull) * gridDim.x;
+      while (ld_acquire_gpu_u64(prm.barrier) < target) { __nanosleep(20); }
+    }
+    named_bar_sync(1, kConsumerThreads);
+    stamp(2);
+    // ---- every CTA combines the per-CTA partials in the same fixed order ---------------------------
+    if (threadIdx.x < 32) {
+      double tot = 0.0;
+      for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) tot += __ldcg(prm.partials + i);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+      if (threadIdx.x == 0) {
+        const float g_norm = __fsqrt_rn((float)tot);        // tf.linalg.global_norm
+        s_bcast[0] = clip_scale(g_norm, prm.sc.clip);
+        s_bcast[1] = g_norm;
+      }
+    }
+    named_bar_sync(1, kConsumerThreads);
+    const float s = s_bcast[0];
+    // ---- pass 2 ----
+    if (C > 0) {
+      TileDesc d = prm.tiles[b + tile_of_q(0) * G];
+      RingPos rp;
+      for (int q = 0; q < C; ++q) {
+        const int j = tile_of_q(q);
+        TileDesc dnx = d;
+        if (q + 1 < C) dnx = prm.tiles[b + tile_of_q(q + 1) * G];
+        const uint32_t tm = (j < n_tm && tmem_ok<HAS_G>(d, prm)) ? tmem_slot_addr(tmem_base, j) : kNoTmem;
+        update_tile2<VARIANT>(d, prm, s, ring + (size_t)rp.slot * kP2SlotVecs, &s_full2[grp][rp.slot], &s_empty2[grp][rp.slot],
+                              rp.use & 1u, tm);
+        rp.advance(kP2Slots);
+        d = dnx;
+      }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      prm.stats[0] = 1.f; prm.stats[1] = prm.sc.lr; prm.stats[2] = s_bcast[1]; prm.stats[3] = s;
     }
   }
   __syncthreads();
-  const float s = s_bcast[0], gn = s_bcast[1];
-  // ---- pass 2: L2-resident tiles youngest first, then the slots, then Tensor Memory ----------------
-  if (!is_producer && tc.count > 0) {
-    auto run = [&](int j) {
-      const TileDesc d = prm.tiles[b + j * G];
-      const bool ok = stashable<HAS_G>(d, prm);
-      const float4* st = (j >= tc.first_st && ok) ? slots + (size_t)(j % M) * kSlotVecs : nullptr;
-      uint32_t tm = kNoTmem;
-      if (j < tc.n_tm && d.len == (uint32_t)kTile && ok) tm = tmem_slot_addr(tmem_base, j);
-      update_tile2<VARIANT>(d, prm, s, st, tm);
-    };
-    for (int j = tc.first_st - 1; j >= tc.n_tm; --j) run(j);
-    for (int j = tc.first_st; j < tc.count; ++j) run(j);
-    for (int j = 0; j < tc.n_tm; ++j) run(j);
-  }
-  __syncthreads();
   stamp(3);
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    prm.stats[0] = 1.f; prm.stats[1] = prm.sc.lr; prm.stats[2] = gn; prm.stats[3] = s;
-  }
   if (prm.tmem_tiles > 0 && warp == 1) tmem_dealloc(tmem_base);
 }
 

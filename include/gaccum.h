@@ -99,8 +99,14 @@ GACCUM_API float gaccum_learning_rate(double init_lr, int64_t num_train_steps,
 /* optimization.py:77,91: the tf.cond predicate, int32(global_step) % N == 0 (pre-increment). */
 GACCUM_API int gaccum_is_apply_step(int64_t global_step, int32_t accum_n);
 /* optimization.py:179-194: decay mask from variable names.  `exclude` are regular expressions
- * searched in the name (POSIX extended; the reference's are plain substrings); a trailing
- * ":<digits>" is stripped from each name first.  out[i] = 1 iff tensor i gets weight decay. */
+ * searched in the name; a trailing ":<digits>" is stripped from each name first.
+ * out[i] = 1 iff tensor i gets weight decay.
+ * DIALECT: POSIX extended (regcomp REG_EXTENDED), the reference uses Python `re.search`
+ * (optimization.py:185).  The two agree on the reference's own patterns ("LayerNorm",
+ * "layer_norm", "bias" -- plain substrings) and on the common subset; Python-only syntax
+ * (\d, \w, look-arounds, non-greedy) is rejected with GACCUM_EINVAL or matches differently.
+ * Callers that accept user patterns should evaluate them with the reference's engine and pass
+ * the resulting mask to gaccum_plan_create -- both Python bindings in this repository do. */
 GACCUM_API int gaccum_decay_mask(int32_t num_tensors, const char* const* names,
                                  double weight_decay_rate, const char* const* exclude,
                                  int32_t num_exclude, uint8_t* out);
