@@ -51,6 +51,12 @@ class DpComm(C.Structure):
                 ("ctrl_peers", C.c_void_p * MAX_RANKS), ("stage_elements", C.c_int64)]
 
 
+class DpIpc(C.Structure):
+    """gaccum_dp_ipc: what one rank's host session exports for the others (plain bytes)."""
+    _fields_ = [("param", C.c_ubyte * 64), ("stage", C.c_ubyte * 64), ("ctrl", C.c_ubyte * 64),
+                ("stage_elements", C.c_int64), ("padded_size", C.c_int64)]
+
+
 class Stats(C.Structure):
     _fields_ = [("applied", C.c_float), ("lr", C.c_float), ("global_norm", C.c_float),
                 ("clip_scale", C.c_float)]
@@ -108,6 +114,8 @@ def _load():
         "gaccum_step_host": (C.c_int, [vp, vp, vp, C.POINTER(StepArgs), vp]),
         "gaccum_host_session_sync": (C.c_int, [vp]),
         "gaccum_host_session_slabs": (C.c_int, [vp, vp]),
+        "gaccum_host_session_dp_export": (C.c_int, [vp, i32, C.POINTER(DpIpc)]),
+        "gaccum_host_session_dp_connect": (C.c_int, [vp, i32, i32, C.POINTER(DpIpc)]),
         "gaccum_dp_shard_range": (C.c_int, [vp, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]),
         "gaccum_dp_stage_elements": (i64, [vp, i32]),
         "gaccum_apply_dp": (C.c_int, [vp, C.POINTER(DpComm), vp, vp, vp, C.POINTER(StepArgs), C.c_uint32, vp]),
@@ -274,6 +282,17 @@ class HostSession:
 
     def sync(self) -> None:
         _check(_load().gaccum_host_session_sync(self._h))
+
+    def dp_export(self, world: int) -> bytes:
+        rec = DpIpc()
+        _check(_load().gaccum_host_session_dp_export(self._h, world, C.byref(rec)))
+        return bytes(rec)
+
+    def dp_connect(self, rank: int, world: int, records: Sequence[bytes]) -> None:
+        arr = (DpIpc * world)()
+        for w, r in enumerate(records):
+            C.memmove(C.byref(arr[w]), r, C.sizeof(DpIpc))
+        _check(_load().gaccum_host_session_dp_connect(self._h, rank, world, arr))
 
     def slabs(self):
         out = (C.c_void_p * 4)()

@@ -61,7 +61,7 @@ struct gaccum_plan {
   double* d_partials = nullptr;
   float* d_stats = nullptr;
   uint32_t* d_dp_sync = nullptr;           // data-parallel kernel: block-completion counters (zero between launches)
-  unsigned long long* d_barrier = nullptr; // clip-apply kernel: monotonic arrival counter of the consumers' grid barrier
+  unsigned long long* d_barrier = nullptr; // clip-apply kernel: [0] monotonic arrival counter of the consumers' grid barrier, [1] tile-pool tickets
   int tmem_tiles = kTmemTiles;             // tiles of a' per consumer group parked in Tensor Memory (GACCUM_TMEM_TILES: A/B)
 #ifdef GACCUM_EXPERIMENTS
   unsigned long long* d_debug = nullptr;   // per-CTA timestamps (tools/cta_timeline.py; experiments build only)
@@ -188,6 +188,7 @@ static int launch_apply_clip(gaccum_plan* pl, KernelParams<CAP>& prm, cudaStream
   // the grid must be the same for every launch on this plan: the consumers' barrier counter advances by gridDim.x
   const int grid = std::max(1, std::min(pl->num_sms, ((int)pl->tiles.size() + kGroups - 1) / kGroups));
   prm.barrier = pl->d_barrier;
+  prm.pool_ticket = pl->d_barrier + 1;
   prm.tmem_tiles = pl->tmem_tiles;
   void* args[] = {(void*)&prm};
   CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kClipThreads), args, (size_t)kRingBytes, st));
@@ -412,8 +413,8 @@ int gaccum_plan_create(gaccum_plan** out, int32_t T, const int64_t* numels, cons
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_partials, sizeof(double) * (size_t)pl->max_grid);
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_dp_sync, sizeof(uint32_t) * 8);
     if (e == cudaSuccess) e = cudaMemset(pl->d_dp_sync, 0, sizeof(uint32_t) * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&pl->d_barrier, sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMemset(pl->d_barrier, 0, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_barrier, 2 * sizeof(unsigned long long));   // [0] barrier arrivals, [1] pool tickets
+    if (e == cudaSuccess) e = cudaMemset(pl->d_barrier, 0, 2 * sizeof(unsigned long long));
 #ifdef GACCUM_EXPERIMENTS
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_debug, sizeof(unsigned long long) * 16 * (size_t)pl->max_grid);
     if (e == cudaSuccess) e = cudaMemset(pl->d_debug, 0, sizeof(unsigned long long) * 16 * (size_t)pl->max_grid);
@@ -642,64 +643,45 @@ int gaccum_step_dp(gaccum_plan* pl, const gaccum_dp_comm* comm, const float* con
 struct gaccum_host_session {
   gaccum_plan* plan = nullptr;
   float *d_params = nullptr, *d_accum = nullptr, *d_m = nullptr, *d_v = nullptr;
-  float* d_stage[2] = {nullptr, nullptr};
+  float* d_stage[2] = {nullptr, nullptr};                    // H2D staging of the gradients, double-buffered
+  std::vector<const float*> stage_ptrs[2];                   // per-tensor views of the staging slabs (pointer table of the DP kernel)
   cudaStream_t compute = nullptr, h2d = nullptr, d2h = nullptr;
   cudaEvent_t buf_free[2] = {nullptr, nullptr}, h2d_done[2] = {nullptr, nullptr}, k_done = nullptr, d2h_done = nullptr;
   uint64_t calls = 0;
-  // zero-copy path: pinned (device-mapped) host gradients are read by the kernel itself over PCIe
-  std::vector<const float*> last_host, dev_alias;
-  std::vector<float*> param_ptrs;
-  bool last_direct = false, force_staged = false, gather_small = false;
-  // staged path: tensors below kGatherBytes are gathered by ONE kernel from pinned host memory instead
-  // of one cudaMemcpyAsync each (46 of BERT-Small's 73 tensors are <= 2 KB; a copy costs ~6 us of gap)
-  std::vector<const float*> g_last, g_alias;
-  bool g_ok = false;
+  // data parallel (gaccum_host_session_dp_export / _connect)
+  int dp_rank = 0, dp_world = 1;
+  float* d_dp_stage = nullptr;                               // this rank's reduce-scatter staging area (peer-written)
+  uint32_t* d_dp_ctrl = nullptr;
+  int64_t dp_stage_elements = 0;
+  gaccum_dp_comm comm{};
+  std::vector<void*> ipc_opened;
+  uint32_t dp_epoch = 0;
 };
-constexpr size_t kGatherBytes = 256 * 1024;
 
-static bool resolve_gather(gaccum_host_session* s, const float* const* host_grads) {
-  gaccum_plan* pl = s->plan;
-  if (!s->gather_small) return false;
-  bool same = (int)s->g_last.size() == pl->T;
-  for (int32_t t = 0; same && t < pl->T; ++t) same = s->g_last[t] == host_grads[t];
-  if (same) return s->g_ok;
-  s->g_last.assign(host_grads, host_grads + pl->T);
-  s->g_alias.assign((size_t)pl->T, nullptr);
-  bool ok = true, any = false;
-  for (int32_t t = 0; t < pl->T && ok; ++t) {
-    if (!host_grads[t] || pl->numel[t] == 0 || (size_t)pl->numel[t] * sizeof(float) > kGatherBytes) continue;
-    cudaPointerAttributes at{};
-    if (cudaPointerGetAttributes(&at, host_grads[t]) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
-    if (at.type != cudaMemoryTypeHost || at.devicePointer == nullptr) { ok = false; break; }
-    s->g_alias[t] = static_cast<const float*>(at.devicePointer);
-    any = true;
+// One cudaMemcpyAsync per RUN of tensors whose host addresses are laid out like the device slab (same distance
+// between consecutive tensors on both sides, padding included): a caller that keeps its gradients / parameters
+// in one pinned arena with the plan's offsets gets a single copy per direction instead of one per tensor
+// (each costs ~6 us of copy-engine gap: 73 copies held the link at 44 GB/s, one copy reaches ~55).
+extern "C++" {
+template <typename HostPtr, typename F>
+static int for_each_run(const gaccum_plan* pl, HostPtr const* host, F&& copy /* (t0, host_ptr, dev_offset, elements) -> cudaError_t */) {
+  int32_t t = 0;
+  while (t < pl->T) {
+    if (pl->numel[t] == 0 || !host[t]) { ++t; continue; }
+    const int32_t t0 = t;
+    int64_t span = pl->numel[t];
+    while (t + 1 < pl->T && host[t + 1] && pl->numel[t + 1] > 0 &&
+           (const float*)host[t + 1] - (const float*)host[t0] == pl->offset[t + 1] - pl->offset[t0]) {
+      ++t;
+      span = pl->offset[t] - pl->offset[t0] + pl->numel[t];
+    }
+    cudaError_t e = copy(t0, host[t0], pl->offset[t0], span);
+    if (e != cudaSuccess) return fail(GACCUM_ECUDA, "host<->device copy failed: %s", cudaGetErrorString(e));
+    ++t;
   }
-  s->g_ok = ok && any;
-  return s->g_ok;
+  return GACCUM_OK;
 }
-
-// Are all gradient buffers pinned host memory the device can address (UVA)?  Then the kernels can
-// consume them in place: no staging copy, no 73 cudaMemcpyAsync per micro-step (each costs ~6 us of
-// copy-engine gap), one PCIe-bound kernel.  Cached on the pointer set.
-static bool resolve_direct(gaccum_host_session* s, const float* const* host_grads) {
-  gaccum_plan* pl = s->plan;
-  if (s->force_staged) return false;
-  bool same = (int)s->last_host.size() == pl->T;
-  for (int32_t t = 0; same && t < pl->T; ++t) same = s->last_host[t] == host_grads[t];
-  if (same) return s->last_direct;
-  s->last_host.assign(host_grads, host_grads + pl->T);
-  s->dev_alias.assign((size_t)pl->T, nullptr);
-  bool direct = true;
-  for (int32_t t = 0; t < pl->T && direct; ++t) {
-    if (!host_grads[t] || pl->numel[t] == 0) continue;
-    cudaPointerAttributes at{};
-    if (cudaPointerGetAttributes(&at, host_grads[t]) != cudaSuccess) { cudaGetLastError(); direct = false; break; }
-    if (at.type != cudaMemoryTypeHost || at.devicePointer == nullptr) { direct = false; break; }
-    s->dev_alias[t] = static_cast<const float*>(at.devicePointer);
-  }
-  s->last_direct = direct;
-  return direct;
-}
+}  // extern "C++"
 
 int gaccum_host_session_destroy(gaccum_host_session* s) {
   if (!s) return GACCUM_OK;
@@ -708,8 +690,9 @@ int gaccum_host_session_destroy(gaccum_host_session* s) {
     if (s->compute) cudaStreamSynchronize(s->compute);
     if (s->h2d) cudaStreamSynchronize(s->h2d);
     if (s->d2h) cudaStreamSynchronize(s->d2h);
+    for (void* p : s->ipc_opened) cudaIpcCloseMemHandle(p);
     cudaFree(s->d_params); cudaFree(s->d_accum); cudaFree(s->d_m); cudaFree(s->d_v);
-    cudaFree(s->d_stage[0]); cudaFree(s->d_stage[1]);
+    cudaFree(s->d_stage[0]); cudaFree(s->d_stage[1]); cudaFree(s->d_dp_stage); cudaFree(s->d_dp_ctrl);
     for (int i = 0; i < 2; ++i) { if (s->buf_free[i]) cudaEventDestroy(s->buf_free[i]); if (s->h2d_done[i]) cudaEventDestroy(s->h2d_done[i]); }
     if (s->k_done) cudaEventDestroy(s->k_done);
     if (s->d2h_done) cudaEventDestroy(s->d2h_done);
@@ -747,15 +730,13 @@ int gaccum_host_session_create(gaccum_host_session** out, gaccum_plan* pl) {
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->k_done, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->d2h_done, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
-  s->param_ptrs.resize((size_t)pl->T);
-  for (int32_t t = 0; t < pl->T; ++t) s->param_ptrs[t] = s->d_params + pl->offset[t];
-  // measured on B200 / PCIe Gen5 (profiles/r01_tune_sweep.md): the copy engines move the large tensors
-  // faster (55 GB/s) than SM loads over PCIe (41 GB/s), so the zero-copy path is opt-in
-  s->force_staged = getenv("GACCUM_HOST_DIRECT") == nullptr;
-  s->gather_small = getenv("GACCUM_HOST_GATHER") != nullptr;   // gathering the small tensors with one kernel: no gain measured, opt-in
   if (e != cudaSuccess) {
     gaccum_host_session_destroy(s);
     return fail(GACCUM_ECUDA, "host session setup failed: %s", cudaGetErrorString(e));
+  }
+  for (int b = 0; b < 2; ++b) {
+    s->stage_ptrs[b].resize((size_t)pl->T);
+    for (int32_t t = 0; t < pl->T; ++t) s->stage_ptrs[b][t] = s->d_stage[b] + pl->offset[t];
   }
   *out = s;
   return GACCUM_OK;
@@ -765,13 +746,67 @@ int gaccum_host_session_set_params(gaccum_host_session* s, const float* const* h
   if (!s || !host_params) return fail(GACCUM_EINVAL, "bad arguments to gaccum_host_session_set_params");
   gaccum_plan* pl = s->plan;
   DeviceGuard guard(pl->device);
-  for (int32_t t = 0; t < pl->T; ++t) {
-    if (pl->numel[t] == 0) continue;
-    if (!host_params[t]) return fail(GACCUM_EINVAL, "host_params[%d] is NULL", t);
-    CUDA_TRY(cudaMemcpyAsync(s->d_params + pl->offset[t], host_params[t], (size_t)pl->numel[t] * sizeof(float),
-                             cudaMemcpyHostToDevice, s->compute));
-  }
+  for (int32_t t = 0; t < pl->T; ++t)
+    if (pl->numel[t] && !host_params[t]) return fail(GACCUM_EINVAL, "host_params[%d] is NULL", t);
+  if (int rc = for_each_run(pl, host_params, [&](int32_t, const float* h, int64_t off, int64_t n) {
+        return cudaMemcpyAsync(s->d_params + off, h, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s->compute);
+      })) return rc;
   CUDA_TRY(cudaStreamSynchronize(s->compute));
+  return GACCUM_OK;
+}
+
+// ---- data parallel over host buffers: every rank's session exports IPC handles of its parameter slab, staging
+//      area and control block; the caller exchanges the (plain-byte) records between the ranks with whatever
+//      transport it has (MPI, torch.distributed, TF collectives) and hands all of them back ----
+int gaccum_host_session_dp_export(gaccum_host_session* s, int32_t world, gaccum_dp_ipc* out) {
+  if (!s || !out) return fail(GACCUM_EINVAL, "bad arguments to gaccum_host_session_dp_export");
+  if (world < 2 || world > GACCUM_MAX_RANKS) return fail(GACCUM_EINVAL, "world must be 2..%d", GACCUM_MAX_RANKS);
+  static_assert(sizeof(cudaIpcMemHandle_t) == GACCUM_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+  gaccum_plan* pl = s->plan;
+  DeviceGuard guard(pl->device);
+  if (!s->d_dp_stage) {
+    s->dp_stage_elements = stage_span(pl, world) * (world - 1);
+    CUDA_TRY(cudaMalloc(&s->d_dp_stage, (size_t)s->dp_stage_elements * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&s->d_dp_ctrl, GACCUM_DP_CTRL_BYTES));
+    CUDA_TRY(cudaMemset(s->d_dp_ctrl, 0, GACCUM_DP_CTRL_BYTES));
+    CUDA_TRY(cudaDeviceSynchronize());
+  }
+  std::memset(out, 0, sizeof *out);
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, s->d_params)); std::memcpy(out->param, &h, sizeof h);
+  CUDA_TRY(cudaIpcGetMemHandle(&h, s->d_dp_stage)); std::memcpy(out->stage, &h, sizeof h);
+  CUDA_TRY(cudaIpcGetMemHandle(&h, s->d_dp_ctrl)); std::memcpy(out->ctrl, &h, sizeof h);
+  out->stage_elements = s->dp_stage_elements;
+  out->padded_size = pl->padded;
+  return GACCUM_OK;
+}
+
+int gaccum_host_session_dp_connect(gaccum_host_session* s, int32_t rank, int32_t world, const gaccum_dp_ipc* all) {
+  if (!s || !all) return fail(GACCUM_EINVAL, "bad arguments to gaccum_host_session_dp_connect");
+  if (world < 2 || world > GACCUM_MAX_RANKS || rank < 0 || rank >= world) return fail(GACCUM_EINVAL, "world must be 2..%d and 0 <= rank < world", GACCUM_MAX_RANKS);
+  if (!s->d_dp_stage) return fail(GACCUM_EINVAL, "call gaccum_host_session_dp_export first");
+  gaccum_plan* pl = s->plan;
+  DeviceGuard guard(pl->device);
+  gaccum_dp_comm c{};
+  c.rank = rank; c.world = world; c.accum = s->d_accum; c.stage_elements = s->dp_stage_elements;
+  for (int w = 0; w < world; ++w) {
+    if (all[w].padded_size != pl->padded || all[w].stage_elements != s->dp_stage_elements)
+      return fail(GACCUM_EINVAL, "rank %d exported a different layout (padded %lld vs %lld): all ranks must use the same plan",
+                  w, (long long)all[w].padded_size, (long long)pl->padded);
+    if (w == rank) { c.param_peers[w] = s->d_params; c.stage_peers[w] = s->d_dp_stage; c.ctrl_peers[w] = s->d_dp_ctrl; continue; }
+    void* ptr[3] = {nullptr, nullptr, nullptr};
+    const unsigned char* src[3] = {all[w].param, all[w].stage, all[w].ctrl};
+    for (int k = 0; k < 3; ++k) {
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, src[k], sizeof h);
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr[k], h, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) return fail(GACCUM_ECUDA, "cudaIpcOpenMemHandle(rank %d, buffer %d) failed: %s (ranks must be GPUs of one NVLink/PCIe peer domain)", w, k, cudaGetErrorString(e));
+      s->ipc_opened.push_back(ptr[k]);
+    }
+    c.param_peers[w] = (float*)ptr[0]; c.stage_peers[w] = (float*)ptr[1]; c.ctrl_peers[w] = (uint32_t*)ptr[2];
+  }
+  s->comm = c;
+  s->dp_rank = rank; s->dp_world = world;
   return GACCUM_OK;
 }
 
@@ -781,74 +816,35 @@ int gaccum_step_host(gaccum_host_session* s, const float* const* host_grads, flo
   if (int rc = check_args(a)) return rc;
   gaccum_plan* pl = s->plan;
   DeviceGuard guard(pl->device);
-  const bool apply_step = gaccum_is_apply_step(a->global_step, a->accum_n) != 0;
-  if (resolve_direct(s, host_grads)) {
-    // ---- zero-copy: the kernel streams the gradients out of pinned host memory ------------------
-    cudaStream_t st = s->compute;
-    int rc;
-    if (apply_step) {
-      rc = pl->T <= kCapSmall
-               ? do_apply_tab<kCapSmall>(pl, s->dev_alias.data(), s->param_ptrs.data(), s->d_accum, s->d_m, s->d_v, a, st)
-               : do_apply_tab<kCapLarge>(pl, s->dev_alias.data(), s->param_ptrs.data(), s->d_accum, s->d_m, s->d_v, a, st);
-    } else {
-      rc = pl->T <= kCapSmall ? do_accumulate_tab<kCapSmall>(pl, s->dev_alias.data(), s->d_accum, a, st)
-                              : do_accumulate_tab<kCapLarge>(pl, s->dev_alias.data(), s->d_accum, a, st);
-    }
-    if (rc) return rc;
-    ++s->calls;
-    if (stats_out)
-      CUDA_TRY(cudaMemcpyAsync(stats_out, pl->d_stats, sizeof(gaccum_stats), cudaMemcpyDeviceToHost, s->compute));
-    if (apply_step && host_params_out) {
-      CUDA_TRY(cudaEventRecord(s->k_done, s->compute));
-      CUDA_TRY(cudaStreamWaitEvent(s->d2h, s->k_done, 0));
-      for (int32_t t = 0; t < pl->T; ++t) {
-        if (pl->numel[t] == 0 || !host_params_out[t]) continue;
-        CUDA_TRY(cudaMemcpyAsync(host_params_out[t], s->d_params + pl->offset[t], (size_t)pl->numel[t] * sizeof(float),
-                                 cudaMemcpyDeviceToHost, s->d2h));
-      }
-      CUDA_TRY(cudaEventRecord(s->d2h_done, s->d2h));
-      CUDA_TRY(cudaStreamWaitEvent(s->compute, s->d2h_done, 0));
-    }
-    return GACCUM_OK;
-  }
   const int b = (int)(s->calls & 1);
   ++s->calls;
   // H2D of this step's gradients into staging buffer b, once the kernel that last read it is done
   CUDA_TRY(cudaStreamWaitEvent(s->h2d, s->buf_free[b], 0));
-  bool any_null = false;
-  const bool gather = resolve_gather(s, host_grads);
-  for (int32_t t = 0; t < pl->T; ++t) {
-    if (pl->numel[t] == 0) continue;
-    if (!host_grads[t]) { any_null = true; continue; }
-    if (gather && s->g_alias[t]) continue;             // picked up by the gather kernel below
-    CUDA_TRY(cudaMemcpyAsync(s->d_stage[b] + pl->offset[t], host_grads[t], (size_t)pl->numel[t] * sizeof(float),
-                             cudaMemcpyHostToDevice, s->h2d));
-  }
-  if (gather) {                                        // one launch for all small tensors: stage = G_host
-    gaccum_step_args ga = *a;
-    int rc = pl->T <= kCapSmall ? do_accumulate_tab<kCapSmall>(pl, s->g_alias.data(), s->d_stage[b], &ga, s->h2d, kFlagAssign)
-                                : do_accumulate_tab<kCapLarge>(pl, s->g_alias.data(), s->d_stage[b], &ga, s->h2d, kFlagAssign);
-    if (rc) return rc;
-  }
-  if (any_null)   // tensors without a gradient contribute nothing (optimization.py:132): stage zeros
-    for (int32_t t = 0; t < pl->T; ++t)
-      if (pl->numel[t] && !host_grads[t])
-        CUDA_TRY(cudaMemsetAsync(s->d_stage[b] + pl->offset[t], 0, (size_t)pl->numel[t] * sizeof(float), s->h2d));
+  if (int rc = for_each_run(pl, host_grads, [&](int32_t, const float* h, int64_t off, int64_t n) {
+        return cudaMemcpyAsync(s->d_stage[b] + off, h, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s->h2d);
+      })) return rc;
+  for (int32_t t = 0; t < pl->T; ++t)     // tensors without a gradient contribute nothing (optimization.py:132): stage zeros
+    if (pl->numel[t] && !host_grads[t])
+      CUDA_TRY(cudaMemsetAsync(s->d_stage[b] + pl->offset[t], 0, (size_t)pl->numel[t] * sizeof(float), s->h2d));
   CUDA_TRY(cudaEventRecord(s->h2d_done[b], s->h2d));
   CUDA_TRY(cudaStreamWaitEvent(s->compute, s->h2d_done[b], 0));
   const bool apply = gaccum_is_apply_step(a->global_step, a->accum_n) != 0;
-  if (int rc = gaccum_step_packed(pl, s->d_stage[b], s->d_params, s->d_accum, s->d_m, s->d_v, a, -1, s->compute)) return rc;
+  if (s->dp_world > 1 && apply) {
+    // 04:55-62 through host buffers: the fused exchange + apply kernel reads this rank's staged gradients
+    if (++s->dp_epoch == 0) s->dp_epoch = 1;
+    if (int rc = gaccum_apply_dp(pl, &s->comm, s->stage_ptrs[b].data(), s->d_m, s->d_v, a, s->dp_epoch, s->compute)) return rc;
+  } else {
+    if (int rc = gaccum_step_packed(pl, s->d_stage[b], s->d_params, s->d_accum, s->d_m, s->d_v, a, -1, s->compute)) return rc;
+  }
   CUDA_TRY(cudaEventRecord(s->buf_free[b], s->compute));
   if (stats_out)
     CUDA_TRY(cudaMemcpyAsync(stats_out, pl->d_stats, sizeof(gaccum_stats), cudaMemcpyDeviceToHost, s->compute));
   if (apply && host_params_out) {
     CUDA_TRY(cudaEventRecord(s->k_done, s->compute));
     CUDA_TRY(cudaStreamWaitEvent(s->d2h, s->k_done, 0));
-    for (int32_t t = 0; t < pl->T; ++t) {
-      if (pl->numel[t] == 0 || !host_params_out[t]) continue;
-      CUDA_TRY(cudaMemcpyAsync(host_params_out[t], s->d_params + pl->offset[t], (size_t)pl->numel[t] * sizeof(float),
-                               cudaMemcpyDeviceToHost, s->d2h));
-    }
+    if (int rc = for_each_run(pl, host_params_out, [&](int32_t, float* h, int64_t off, int64_t n) {
+          return cudaMemcpyAsync(h, s->d_params + off, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->d2h);
+        })) return rc;
     CUDA_TRY(cudaEventRecord(s->d2h_done, s->d2h));
     CUDA_TRY(cudaStreamWaitEvent(s->compute, s->d2h_done, 0));   // the next apply must not overwrite params mid-copy
   }

@@ -89,6 +89,7 @@ struct KernelParams {
   float* stats;       // gaccum_stats
   uint32_t flags;     // kFlag* bits (all of them produce correct results)
   unsigned long long* barrier;  // apply_clip_kernel: monotonic arrival counter of the consumers' grid barrier
+  unsigned long long* pool_ticket;  // apply_clip_kernel: monotonic ticket counter of pass 2's tile pool
   int32_t tmem_tiles;   // apply_clip_kernel: tiles of a' each consumer group parks in Tensor Memory (0..kTmemTiles)
 #ifdef GACCUM_EXPERIMENTS
   unsigned long long* debug;  // 16 words per CTA: 4 timestamps (ns) + wait-cycle counters (tools/cta_timeline.py)
@@ -387,15 +388,21 @@ constexpr int kTmemColsPerWarp = 80;              // 6 warps share a lane quadra
 constexpr int kTmemTiles = kTmemColsPerWarp / 8;  // 10 tiles per group
 constexpr uint32_t kNoTmem = 0xffffffffu;
 #ifndef GACCUM_P1_SLOTS
-#define GACCUM_P1_SLOTS 3
+#define GACCUM_P1_SLOTS 4
 #endif
 constexpr int kP1Slots = GACCUM_P1_SLOTS;         // pass-1 ring slots per group, 16 KB each
 constexpr int kP1SlotVecs = 2 * (kTile / 4);      // float4 per pass-1 slot: G | a
-constexpr int kP2SlotVecs = 3 * (kTile / 4);      // float4 per pass-2 slot: p | m | v
+constexpr int kP2SlotVecs = 4 * (kTile / 4);      // float4 per pass-2 slot: p | m | v | a'
 constexpr int kRingVecs = kP1Slots * kP1SlotVecs; // per group
-constexpr int kP2Slots = kRingVecs / kP2SlotVecs; // 3 x 16 KB = 48 KB -> 2 x 24 KB
-constexpr int kRingBytes = kGroups * kRingVecs * 16;   // dynamic shared memory of the kernel (144 KB)
-static_assert(kP2Slots >= 1 && kP1Slots <= 8, "ring must hold at least one [p|m|v] slot");
+constexpr int kP2Slots = kRingVecs / kP2SlotVecs; // 4 x 16 KB = 64 KB -> 2 x 32 KB
+constexpr int kRingBytes = kGroups * kRingVecs * 16;   // dynamic shared memory of the kernel (192 KB)
+static_assert(kP2Slots >= 1 && kP1Slots <= 8, "ring must hold at least one [p|m|v|a'] slot");
+// what the producer tells the consumers about the tile it put into a pass-2 slot
+struct __align__(16) SlotMeta {
+  TileDesc d;          // len == 0: end of pass 2
+  uint32_t tmem_slot;  // a' is parked in this Tensor-Memory slot of the group (kNoTmem: it is in the slot's 4th quarter / in global memory)
+  uint32_t pad[3];
+};
 constexpr int kMaxSlots = 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -559,10 +566,11 @@ __device__ __forceinline__ float norm_tile(const TileDesc& d, const KernelParams
   return acc;
 }
 
-// ---- pass 2, consumer side: one tile out of slot [p | m | v]; a' from Tensor Memory or from L2 ----------
+// ---- pass 2, consumer side: one tile out of slot [p | m | v | a']; a' from the slot or from Tensor Memory ----
+// The caller has waited on the slot's `full` barrier (it had to, to learn which tile this is).
 template <int VARIANT, int CAP>
 __device__ __forceinline__ void update_tile2(const TileDesc& d, const KernelParams<CAP>& prm, const float s, const float4* slot,
-                                             uint64_t* full, uint64_t* empty, const uint32_t parity, const uint32_t tmem) {
+                                             uint64_t* empty, const uint32_t tmem) {
   const size_t soff = (size_t)d.soff32 * kSlabAlign;
   float* __restrict__ a = prm.accum + soff;
   float* __restrict__ m = prm.m + soff;
@@ -582,20 +590,14 @@ __device__ __forceinline__ void update_tile2(const TileDesc& d, const KernelPara
     float4* v4 = reinterpret_cast<float4*>(v);
     float4* p4 = reinterpret_cast<float4*>(p);
     float4 va[kUnroll], vp[kUnroll], vm[kUnroll], vv[kUnroll];
-    if (tmem == kNoTmem) {                      // a' comes back from L2 (evict_last since pass 1): issue before waiting
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        const uint32_t i = u * kThreads + tid;
-        if (i < nvec) va[u] = __ldcs(a4 + i);
-      }
-    } else {
-      tmem_load8(tmem, va[0], va[1]);
-    }
-    mbar_wait(full, parity);                    // p, m, v have landed
+    if (tmem != kNoTmem) tmem_load8(tmem, va[0], va[1]);
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const uint32_t i = u * kThreads + tid;
-      if (i < nvec) { vp[u] = slot[i]; vm[u] = slot[kTile / 4 + i]; vv[u] = slot[2 * (kTile / 4) + i]; }
+      if (i < nvec) {
+        vp[u] = slot[i]; vm[u] = slot[kTile / 4 + i]; vv[u] = slot[2 * (kTile / 4) + i];
+        if (tmem == kNoTmem) va[u] = slot[3 * (kTile / 4) + i];
+      }
     }
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(empty);
@@ -616,7 +618,6 @@ __device__ __forceinline__ void update_tile2(const TileDesc& d, const KernelPara
       p[i] = px; m[i] = mx; v[i] = vx; a[i] = 0.f;
     }
   } else {
-    mbar_wait(full, parity);
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(empty);
     for (uint32_t i = tid; i < len; i += kThreads) {
@@ -650,6 +651,8 @@ apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
   __shared__ uint32_t s_tmem_base;
   __shared__ __align__(8) uint64_t s_full1[kGroups][kMaxSlots], s_empty1[kGroups][kMaxSlots];
   __shared__ __align__(8) uint64_t s_full2[kGroups][kMaxSlots], s_empty2[kGroups][kMaxSlots];
+  __shared__ __align__(8) uint64_t s_go[kGroups];
+  __shared__ SlotMeta s_meta[kGroups][kMaxSlots];
 
   const int warp = (int)threadIdx.x >> 5;
   const bool is_producer = warp >= kConsumerThreads / 32;
@@ -660,8 +663,6 @@ apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
   const int n_tm = min(prm.tmem_tiles, C);                         // tiles j < n_tm park a' in Tensor Memory
   float4* const ring = reinterpret_cast<float4*>(smem_dyn) + (size_t)grp * kRingVecs;
   const uint64_t pol_last = policy_evict_last();
-  // pass 2 order: L2-resident tiles youngest first (q = 0 -> j = C-1), then the Tensor-Memory tiles
-  auto tile_of_q = [&](int q) { return q < C - n_tm ? C - 1 - q : q - (C - n_tm); };
 
 #ifdef GACCUM_EXPERIMENTS
   auto stamp = [&](int which) {
@@ -682,6 +683,7 @@ apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
     for (int g = 0; g < kGroups; ++g) {
       for (int sl = 0; sl < kP1Slots; ++sl) { mbar_init(&s_full1[g][sl], 1); mbar_init(&s_empty1[g][sl], kThreads / 32); }
       for (int sl = 0; sl < kP2Slots; ++sl) { mbar_init(&s_full2[g][sl], 1); mbar_init(&s_empty2[g][sl], kThreads / 32); }
+      mbar_init(&s_go[g], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -755,41 +757,66 @@ apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
       prm.debug[blockIdx.x * 16 + 13 + grp] = (unsigned long long)(clock64() - dbg_p0);   // cycles until pass 1 was issued and drained
     }
 #endif
-    // ---- pass 2: [p | m | v] in pass-2 order.  Nothing here depends on the clip scale: no grid barrier ----
-    {
-      auto fetch = [&](int q0, TileDesc& d) { const int q = q0 + lane; if (q < C) d = prm.tiles[b + tile_of_q(q) * G]; };
-      TileDesc dc{}, dn{};
-      fetch(0, dc); fetch(32, dn);
+    // ---- pass 2.  First the group's own Tensor-Memory tiles (their a' cannot move; their p, m, v do not depend on
+    //      the clip scale, so these copies start BEFORE the grid barrier and HBM stays busy while the CTAs wait for
+    //      each other).  Then tiles out of the GLOBAL POOL of L2-resident tiles, youngest first, one atomic ticket per
+    //      tile: SMs that get a larger share of the saturated memory system simply take more tickets, so all SMs
+    //      finish together (with static tiles the slowest SM finished 40 us after the fastest).  Pool tiles carry
+    //      their a' in the slot's 4th quarter; they may only be fetched once every CTA has passed the barrier. ----
+    if (lane == 0) {
       RingPos rp;
-      for (int q0 = 0; q0 < C; q0 += 32) {
-        const int nb = min(32, C - q0);
-        for (int l = 0; l < nb; ++l) {
-          TileDesc d;
-          d.tensor_flags = __shfl_sync(0xffffffffu, dc.tensor_flags, l);
-          d.len = __shfl_sync(0xffffffffu, dc.len, l);
-          d.toff = __shfl_sync(0xffffffffu, dc.toff, l);
-          d.soff32 = __shfl_sync(0xffffffffu, dc.soff32, l);
-          if (lane == 0) {
-            const float* p = param_ptr(prm.tab, d);
-            const uint32_t nvec = bulk_vecs2(d, p);
-            uint64_t* full = &s_full2[grp][rp.slot];
-            mbar_wait(&s_empty2[grp][rp.slot], (rp.use & 1u) ^ 1u);
-            if (nvec > 0) {
-              const size_t soff = (size_t)d.soff32 * kSlabAlign;
-              float4* dst = ring + (size_t)rp.slot * kP2SlotVecs;
-              mbar_arrive_expect_tx(full, nvec * 48u);
-              bulk_g2s(dst, p, nvec * 16u, full, pol_first);
-              bulk_g2s(dst + kTile / 4, prm.m + soff, nvec * 16u, full, pol_first);
-              bulk_g2s(dst + 2 * (kTile / 4), prm.v + soff, nvec * 16u, full, pol_first);
-            } else {
-              mbar_arrive(full);
-            }
+      const int pool_lo = prm.tmem_tiles * G;                                   // tiles [pool_lo, nt) form the pool
+      const unsigned long long pool_n = (unsigned long long)max(0, nt - pool_lo);
+      const unsigned long long draws = pool_n + (unsigned long long)G;          // per launch: every producer over-draws exactly once
+      int jb = 0;                                                               // next own Tensor-Memory tile
+      bool past_barrier = false;
+      while (true) {
+        int tile;
+        uint32_t tmem_slot = kNoTmem;
+        auto wait_for_barrier = [&]() {
+          if (!past_barrier) {
+            mbar_wait(&s_go[grp], 0);                                           // the consumers are through the grid barrier
+            asm volatile("fence.proxy.async;" ::: "memory");                    // generic-proxy a' stores -> our bulk reads
+            past_barrier = true;
           }
-          rp.advance(kP2Slots);
+        };
+        if (jb < n_tm) {
+          tile = b + jb * G;
+          tmem_slot = (uint32_t)jb;
+          ++jb;
+        } else {
+          wait_for_barrier();
+          const unsigned long long tk = atomicAdd(prm.pool_ticket, 1ull) % draws;
+          if (tk >= pool_n) break;
+          tile = nt - 1 - (int)tk;                                              // youngest a' lines first
         }
-        dc = dn;
-        fetch(q0 + 64, dn);
+        const TileDesc d = prm.tiles[tile];
+        const float* p = param_ptr(prm.tab, d);
+        const uint32_t nvec = bulk_vecs2(d, p);
+        const bool in_tmem = tmem_slot != kNoTmem && tmem_ok<HAS_G>(d, prm);
+        if (!in_tmem) wait_for_barrier();                                       // a' of this tile is in global memory: complete only after pass 1
+        uint64_t* full = &s_full2[grp][rp.slot];
+        mbar_wait(&s_empty2[grp][rp.slot], (rp.use & 1u) ^ 1u);
+        SlotMeta* meta = &s_meta[grp][rp.slot];
+        meta->d = d;
+        meta->tmem_slot = in_tmem ? tmem_slot : kNoTmem;
+        if (nvec > 0) {
+          const size_t soff = (size_t)d.soff32 * kSlabAlign;
+          float4* dst = ring + (size_t)rp.slot * kP2SlotVecs;
+          mbar_arrive_expect_tx(full, nvec * 16u * (in_tmem ? 3u : 4u));
+          bulk_g2s(dst, p, nvec * 16u, full, pol_first);
+          bulk_g2s(dst + kTile / 4, prm.m + soff, nvec * 16u, full, pol_first);
+          bulk_g2s(dst + 2 * (kTile / 4), prm.v + soff, nvec * 16u, full, pol_first);
+          if (!in_tmem) bulk_g2s(dst + 3 * (kTile / 4), prm.accum + soff, nvec * 16u, full, pol_first);
+        } else {
+          mbar_arrive(full);
+        }
+        rp.advance(kP2Slots);
       }
+      // end marker
+      mbar_wait(&s_empty2[grp][rp.slot], (rp.use & 1u) ^ 1u);
+      s_meta[grp][rp.slot].d.len = 0;
+      mbar_arrive(&s_full2[grp][rp.slot]);
     }
     __syncwarp();
   } else {
@@ -832,6 +859,7 @@ apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
       while (ld_acquire_gpu_u64(prm.barrier) < target) { __nanosleep(20); }
     }
     named_bar_sync(1, kConsumerThreads);
+    if ((threadIdx.x & (kThreads - 1)) == 0) mbar_arrive(&s_go[grp]);    // this group's producer may now fetch pool tiles
     stamp(2);
     // ---- every CTA combines the per-CTA partials in the same fixed order ---------------------------
     if (threadIdx.x < 32) {
@@ -847,19 +875,16 @@ apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
     }
     named_bar_sync(1, kConsumerThreads);
     const float s = s_bcast[0];
-    // ---- pass 2 ----
-    if (C > 0) {
-      TileDesc d = prm.tiles[b + tile_of_q(0) * G];
+    // ---- pass 2: whatever tiles the producer hands over, until its end marker ----
+    {
       RingPos rp;
-      for (int q = 0; q < C; ++q) {
-        const int j = tile_of_q(q);
-        TileDesc dnx = d;
-        if (q + 1 < C) dnx = prm.tiles[b + tile_of_q(q + 1) * G];
-        const uint32_t tm = (j < n_tm && tmem_ok<HAS_G>(d, prm)) ? tmem_slot_addr(tmem_base, j) : kNoTmem;
-        update_tile2<VARIANT>(d, prm, s, ring + (size_t)rp.slot * kP2SlotVecs, &s_full2[grp][rp.slot], &s_empty2[grp][rp.slot],
-                              rp.use & 1u, tm);
+      while (true) {
+        mbar_wait(&s_full2[grp][rp.slot], rp.use & 1u);
+        const SlotMeta meta = s_meta[grp][rp.slot];
+        if (meta.d.len == 0) break;
+        const uint32_t tm = meta.tmem_slot != kNoTmem ? tmem_slot_addr(tmem_base, (int)meta.tmem_slot) : kNoTmem;
+        update_tile2<VARIANT>(meta.d, prm, s, ring + (size_t)rp.slot * kP2SlotVecs, &s_empty2[grp][rp.slot], tm);
         rp.advance(kP2Slots);
-        d = dnx;
       }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {

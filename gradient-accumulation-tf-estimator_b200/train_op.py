@@ -253,10 +253,41 @@ class HostTrainOp:
     updated parameters come back D2H on apply steps, the 16-byte stats block every step.
     ``host_params`` are updated in place; pin them (and the gradients) for asynchronous copies."""
 
+    @staticmethod
+    def pinned_arena(shapes: Sequence[Sequence[int]], hp: HParams):
+        """One pinned host buffer laid out like the device slabs (plan offsets, 128-byte aligned tensors) and the
+        per-tensor views into it.  Gradients / parameters kept in such an arena cross PCIe with ONE copy per
+        direction (gaccum_step_host coalesces tensors whose host spacing equals their slab spacing)."""
+        numels = [int(np.prod(s)) for s in shapes]
+        layout = Plan(numels, None, hp, device=-1)
+        flat = torch.zeros(max(layout.padded_size, 32), dtype=torch.float32)
+        try:
+            flat = flat.pin_memory()
+        except Exception:
+            pass
+        views = [flat[o:o + n].view(tuple(s)) for o, n, s in zip(layout.offsets, numels, shapes)]
+        return flat, views
+
+    def connect_data_parallel(self, process_group=None) -> None:
+        """04's MultiWorkerMirroredStrategy for host-resident tensors: exchange the sessions' CUDA-IPC records over
+        torch.distributed (any transport would do: they are plain bytes) and switch the apply step to the fused
+        exchange + apply kernel.  Every rank must hold identical parameters and step in lock-step."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+        if world < 2:
+            return
+        mine = self.session.dp_export(world)
+        records = [None] * world
+        dist.all_gather_object(records, mine, group=process_group)
+        self.session.dp_connect(rank, world, records)
+        dist.barrier(group=process_group)
+        self.world = world
+
     def __init__(self, host_params: Sequence[torch.Tensor], names: Sequence[str], hp: HParams, accum_n: int,
                  lr_fn: Callable[[int], float],
                  exclude_from_weight_decay: Optional[Sequence[str]] = ("LayerNorm", "layer_norm", "bias"),
                  global_step: int = 0, device: int = 0):
+        self.world = 1
         for p in host_params:
             if p.device.type != "cpu" or p.dtype != torch.float32 or not p.is_contiguous():
                 raise ValueError("host_params must be contiguous fp32 CPU tensors")

@@ -216,6 +216,28 @@ GACCUM_API int gaccum_step_host(gaccum_host_session* s, const float* const* host
                                 float* const* host_params_out, const gaccum_step_args* args,
                                 gaccum_stats* stats_out);
 GACCUM_API int gaccum_host_session_sync(gaccum_host_session* s);
+/* Copies are coalesced: a run of tensors whose host addresses are spaced like their slab offsets
+ * (gaccum_offsets; padding included) moves with ONE cudaMemcpyAsync, so a caller that keeps its
+ * gradients / parameters in a pinned arena with the plan's layout pays one copy per direction.
+ *
+ * Data parallel over host buffers (reference 04 with CPU-resident tensors): every rank creates a
+ * session, calls _dp_export, the caller exchanges the records between the ranks with whatever
+ * transport it has (MPI, torch.distributed, TF collectives -- they are plain bytes), every rank calls
+ * _dp_connect with all of them.  From then on the apply step of gaccum_step_host is the fused
+ * exchange + apply kernel of gaccum_apply_dp over CUDA-IPC peer mappings of the other ranks'
+ * parameter slabs / staging areas; accumulate steps stay rank-local.  All ranks must step in
+ * lock-step (same global_step, same accum_n).  Ranks must be GPUs of one peer-access domain. */
+#define GACCUM_IPC_HANDLE_BYTES 64
+typedef struct gaccum_dp_ipc {
+  unsigned char param[GACCUM_IPC_HANDLE_BYTES]; /* cudaIpcMemHandle_t of the parameter slab */
+  unsigned char stage[GACCUM_IPC_HANDLE_BYTES]; /* ... of the reduce-scatter staging area */
+  unsigned char ctrl[GACCUM_IPC_HANDLE_BYTES];  /* ... of the control block */
+  int64_t stage_elements;
+  int64_t padded_size;
+} gaccum_dp_ipc;
+GACCUM_API int gaccum_host_session_dp_export(gaccum_host_session* s, int32_t world, gaccum_dp_ipc* out);
+GACCUM_API int gaccum_host_session_dp_connect(gaccum_host_session* s, int32_t rank, int32_t world,
+                                              const gaccum_dp_ipc* all /* world records, rank order */);
 /* device pointers of the resident slabs (params, accum, m, v) for inspection: out[4] */
 GACCUM_API int gaccum_host_session_slabs(gaccum_host_session* s, float** out);
 

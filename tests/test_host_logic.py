@@ -59,8 +59,23 @@ def test_decay_mask_matches_reference_regex_logic():
     assert g.decay_mask(names, 0.0) == [False] * len(names)               # `if not self.weight_decay_rate`
     assert g.decay_mask(["a/bias"], 0.01, exclude=[]) == [True]
     assert g.decay_mask(["layer_3/w", "layer_12/w"], 0.01, exclude=[r"layer_[0-9]+/"]) == [False, False]
-    with pytest.raises(g.GaccumError):
+    # the Python bindings evaluate the patterns with the reference's own engine (re.search, optimization.py:185):
+    # Python-only syntax works exactly as it does in the reference
+    assert g.decay_mask(["layer_3/w", "layer_x/w", "enc/w"], 0.01, exclude=[r"layer_\d+/", r"^(?!layer)"]) == [False, True, False]
+    import re
+    with pytest.raises(re.error):
         g.decay_mask(["a"], 0.01, exclude=["("])
+
+
+def test_c_decay_mask_is_posix_ere_and_agrees_on_the_reference_patterns():
+    """gaccum_decay_mask (for non-Python callers) speaks POSIX ERE: identical on the reference's plain substrings and
+    on the common regex subset; Python-only syntax is documented as different (include/gaccum.h)."""
+    from gaccum_b200 import _lib
+    names = [n for n, _ in onp.MANIFESTS["bert_small"]()] + ["x/layer_norm/w:0", "dense/bias:12", "a:b", "plain"]
+    assert _lib.decay_mask_c(names, 0.01) == g.decay_mask(names, 0.01)
+    assert _lib.decay_mask_c(["layer_3/w", "layer_12/w"], 0.01, exclude=[r"layer_[0-9]+/"]) == [False, False]
+    with pytest.raises(g.GaccumError):
+        _lib.decay_mask_c(["a"], 0.01, exclude=["("])
 
 
 @pytest.mark.parametrize("model,T,P", [("mnist_cnn", 6, 347146), ("bert_small", 73, 28764674),

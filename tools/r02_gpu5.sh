@@ -1,0 +1,15 @@
+#!/bin/bash
+# v5 clip-apply (TMA-fed, dynamic tile pool in pass 2): parity, timeline, A/B
+mkdir -p gpurun_out
+L=gradient-accumulation-tf-estimator_b200/csrc
+B="python bench.py --steps 400 --warmup 10 --e2e-steps 0 --model-steps 0 --cpu-budget 0 --parity-steps 0"
+summ() { python -c "import json,sys; d=json.loads([l for l in sys.stdin if l.startswith('{')][-1]); print('$1', round(d['value']), 'apply_us', round(d['roofline']['avg_launch_us'],1), 'frac', round(d['roofline']['frac'],3), 'acc_us', round(d['roofline_accumulate']['avg_launch_us'],1), d['clocks']['sm_mhz'], d['clocks']['reasons'])"; }
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+echo "== timeline"; timeout 300 python tools/cta_timeline.py 2>&1 | tail -12
+timeout 300 $B 2>/dev/null | summ "v5 p1slots=4"
+GACCUM_LIB=$L/libgaccum_p1s2.so timeout 300 $B 2>/dev/null | summ "v5 p1slots=2 (1 pass-2 slot)"
+for t in 0 5 8; do GACCUM_TMEM_TILES=$t timeout 300 $B 2>/dev/null | summ "v5 tmem_tiles=$t"; done
+timeout 300 $B --workload bert_base 2>/dev/null | summ "v5 bert_base"
+timeout 300 $B --workload bert_large --steps 128 2>/dev/null | summ "v5 bert_large"
+timeout 300 $B --workload mnist_cnn 2>/dev/null | summ "v5 mnist"
+timeout 600 python bench.py --steps 20 --warmup 3 2>gpurun_out/r02e_err_default.log | tee gpurun_out/r02e_bench_default.json | summ "driver-like"
