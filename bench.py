@@ -391,14 +391,26 @@ def run_b200_arm(args):
             numa = f"pinned buffers first-touched on the GPU-local CPUs ({len(os.sched_getaffinity(0))} of {len(old_aff)})"
         except Exception:
             old_aff = None
-        host_params = [(torch.randn(s) * 0.02).pin_memory() for _, s in man]
-        host_grads = [[torch.randn(s).mul_(args.sigma).pin_memory() for _, s in man] for _ in range(2)]
+        # the caller keeps parameters and gradients in pinned ARENAS laid out like the device slabs (plan offsets):
+        # gaccum_step_host then moves each direction with one copy instead of one per tensor
+        shapes = [s for _, s in man]
+        pflat, host_params = HostTrainOp.pinned_arena(shapes, hp)
+        gen_h = torch.Generator(); gen_h.manual_seed(7)             # identical replicas on every rank
+        for hp_t in host_params:
+            hp_t.copy_(torch.randn(hp_t.shape, generator=gen_h) * 0.02)
+        host_grads = []
+        for _ in range(2):
+            gflat, views = HostTrainOp.pinned_arena(shapes, hp)
+            gflat.normal_(0, args.sigma / world)                    # 04:46 loss / num_workers
+            host_grads.append(views)
         if old_aff is not None and not args.e2e_keep_affinity:
             os.sched_setaffinity(0, old_aff)
-        hop = HostTrainOp(host_params, names, hp, N, lr_fn, global_step=START_STEP, device=local)
+        hop = HostTrainOp(host_params, names, hp, N, lr_fn, global_step=START_STEP - START_STEP % N + 1, device=local)
+        if world > 1:
+            hop.connect_data_parallel()        # 04:55-62: the apply step becomes the fused NVLink exchange + apply kernel
         hb = [hop.bind(hg) for hg in host_grads]
-        Ke = args.e2e_steps
-        for i in range(4):
+        Ke = -(-args.e2e_steps // N) * N       # whole windows
+        for i in range(N):
             hop.run_bound(hb[i % 2])
         hop.sync()
         if dist is not None:
@@ -417,8 +429,10 @@ def run_b200_arm(args):
                "h2d_bytes_per_step": 4 * P, "d2h_bytes_per_step": int(4 * P * napply / Ke) + 16,
                "steps": Ke, "ms_per_step": ms / Ke, "api": "gaccum_step_host (C ABI) via HostTrainOp.run_bound",
                "host_memory": numa,
-               "note": "pinned host gradients H2D every micro-step; stats D2H every step; parameters D2H on apply steps; "
-                       "replicas are independent at N>1 (no exchange on this path)"}
+               "note": "pinned host gradients H2D every micro-step (one coalesced copy: arena in slab layout); stats D2H every step; "
+                       "parameters D2H on apply steps" + ("" if world == 1 else
+                       f"; data parallel over {world} ranks: the apply step is the fused NVLink exchange + apply kernel over CUDA-IPC "
+                       "peer mappings (gaccum_host_session_dp_connect), accumulate steps are rank-local")}
         del hop
 
     # ---- with the model in the loop: PyTorch BERT forward/backward (NOT our path) produces the

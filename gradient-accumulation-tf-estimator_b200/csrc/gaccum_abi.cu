@@ -61,7 +61,9 @@ struct gaccum_plan {
   double* d_partials = nullptr;
   float* d_stats = nullptr;
   uint32_t* d_dp_sync = nullptr;           // data-parallel kernel: block-completion counters (zero between launches)
-  unsigned long long* d_barrier = nullptr; // clip-apply kernel: [0] monotonic arrival counter of the consumers' grid barrier, [1] tile-pool tickets
+  unsigned long long* d_barrier = nullptr; // clip-apply kernel: monotonic arrival counter of the consumers' grid barrier
+  LaunchCounters* d_counters = nullptr;    // ... two sets of per-launch counters (tickets, pool length, norm accumulator)
+  uint32_t* d_pool_list = nullptr;         // ... one flag per tile: a' parked in Tensor Memory between the passes
   int tmem_tiles = kTmemTiles;             // tiles of a' per consumer group parked in Tensor Memory (GACCUM_TMEM_TILES: A/B)
 #ifdef GACCUM_EXPERIMENTS
   unsigned long long* d_debug = nullptr;   // per-CTA timestamps (tools/cta_timeline.py; experiments build only)
@@ -188,7 +190,8 @@ static int launch_apply_clip(gaccum_plan* pl, KernelParams<CAP>& prm, cudaStream
   // the grid must be the same for every launch on this plan: the consumers' barrier counter advances by gridDim.x
   const int grid = std::max(1, std::min(pl->num_sms, ((int)pl->tiles.size() + kGroups - 1) / kGroups));
   prm.barrier = pl->d_barrier;
-  prm.pool_ticket = pl->d_barrier + 1;
+  prm.counters = pl->d_counters;
+  prm.parked = pl->d_pool_list;
   prm.tmem_tiles = pl->tmem_tiles;
   void* args[] = {(void*)&prm};
   CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kClipThreads), args, (size_t)kRingBytes, st));
@@ -295,7 +298,7 @@ static int check_args(const gaccum_step_args* a) {
 }
 
 static void free_plan_device(gaccum_plan* pl) {
-  cudaFree(pl->d_tiles); cudaFree(pl->d_partials); cudaFree(pl->d_stats); cudaFree(pl->d_dp_sync); cudaFree(pl->d_barrier);
+  cudaFree(pl->d_tiles); cudaFree(pl->d_partials); cudaFree(pl->d_stats); cudaFree(pl->d_dp_sync); cudaFree(pl->d_barrier); cudaFree(pl->d_counters); cudaFree(pl->d_pool_list);
 #ifdef GACCUM_EXPERIMENTS
   cudaFree(pl->d_debug);
 #endif
@@ -413,8 +416,11 @@ int gaccum_plan_create(gaccum_plan** out, int32_t T, const int64_t* numels, cons
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_partials, sizeof(double) * (size_t)pl->max_grid);
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_dp_sync, sizeof(uint32_t) * 8);
     if (e == cudaSuccess) e = cudaMemset(pl->d_dp_sync, 0, sizeof(uint32_t) * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&pl->d_barrier, 2 * sizeof(unsigned long long));   // [0] barrier arrivals, [1] pool tickets
-    if (e == cudaSuccess) e = cudaMemset(pl->d_barrier, 0, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_barrier, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(pl->d_barrier, 0, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_counters, 2 * sizeof(LaunchCounters));
+    if (e == cudaSuccess) e = cudaMemset(pl->d_counters, 0, 2 * sizeof(LaunchCounters));
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_pool_list, sizeof(uint32_t) * std::max<size_t>(1, pl->tiles.size()));
 #ifdef GACCUM_EXPERIMENTS
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_debug, sizeof(unsigned long long) * 16 * (size_t)pl->max_grid);
     if (e == cudaSuccess) e = cudaMemset(pl->d_debug, 0, sizeof(unsigned long long) * 16 * (size_t)pl->max_grid);

@@ -89,7 +89,8 @@ struct KernelParams {
   float* stats;       // gaccum_stats
   uint32_t flags;     // kFlag* bits (all of them produce correct results)
   unsigned long long* barrier;  // apply_clip_kernel: monotonic arrival counter of the consumers' grid barrier
-  unsigned long long* pool_ticket;  // apply_clip_kernel: monotonic ticket counter of pass 2's tile pool
+  struct LaunchCounters* counters;  // apply_clip_kernel: two sets of per-launch counters (tickets, pool length, norm accumulator)
+  uint32_t* parked;             // apply_clip_kernel: num_tiles flags written in pass 1: 1 = a' of the tile is parked in some SM's Tensor Memory
   int32_t tmem_tiles;   // apply_clip_kernel: tiles of a' each consumer group parks in Tensor Memory (0..kTmemTiles)
 #ifdef GACCUM_EXPERIMENTS
   unsigned long long* debug;  // 16 words per CTA: 4 timestamps (ns) + wait-cycle counters (tools/cta_timeline.py)
@@ -355,9 +356,6 @@ __device__ __forceinline__ double block_reduce_to_double(double x, double* smem 
 // apply with clipping: ONE cooperative launch, one CTA per SM =
 //     3 consumer groups x 256 threads  +  3 producer warps (one per group)          (864 threads)
 //
-// Every consumer group behaves like an independent 256-thread CTA with virtual block id
-// b = blockIdx * 3 + group and owns tiles b, b + 3*grid, b + 6*grid, ...  (its sequence j = 0..C-1).
-//
 // NO consumer ever issues a bulk load: every input stream of both passes is moved by TMA
 // (cp.async.bulk shared <- global, completing on an mbarrier by byte count) into a per-group ring in
 // shared memory, fed by the group's producer warp.  Why (measured, profiles/r02_tune_sweep.md):
@@ -365,20 +363,30 @@ __device__ __forceinline__ double block_reduce_to_double(double x, double* smem 
 //     in; L1 and shared memory split 256 KB, so every KB of on-chip stash was paid for with bytes in
 //     flight (round 1: pass 1 at 4.6 TB/s with 192 KB of stash and 60 KB of L1);
 //   * TMA loads need neither registers nor L1: bytes in flight = ring size, descriptors and addresses are
-//     computed by one lane per group far ahead of the consumers, and the consumers' loop is
-//     wait -> LDS -> math -> store.
-// pass 1   ring slot = [G tile | a tile] (16 KB, kP1Slots per group).  a' = a + G, reduce sum((a'/N)^2)
-//          (thread fp32 per tile -> fp64 running sum -> warp shuffle -> shared memory -> one fp64 partial
-//          per CTA).  a' of the group's first kTmemTiles tiles is parked in Tensor Memory (tcgen05.st: 256 KB
-//          per SM that a kernel without MMA leaves idle), the rest goes back in place tagged L2::evict_last.
+//     computed by the producers ahead of the consumers, whose loop is wait -> LDS -> math -> store.
+// NO tile is bound to an SM before it is fetched: with the memory system saturated some SMs get a larger share
+// of it than others (with static tiles the first SM finished pass 2 forty microseconds before the last), so the
+// producers draw tiles from global atomic ticket counters -- every SM stays busy until the pass is over.
+//
+// pass 1   tickets over ALL tiles.  ring slot = [G tile | a tile] (16 KB, kP1Slots per group).  a' = a + G;
+//          sum((a'/N)^2): thread fp32 per tile -> warp shuffle in fp64 (fixed order) -> EXACT accumulation of the
+//          per-warp, per-tile sums in a 2176-bit fixed-point accumulator (integer atomics: associative, so the
+//          total does not depend on which SM reduced which tile -- the norm is bit-identical from run to run
+//          and across replicas although the schedule is dynamic).  a' of the first kTmemTiles tiles a group
+//          processes is parked in Tensor Memory (tcgen05.st: 256 KB per SM that a kernel without MMA leaves
+//          idle) and the tile is remembered in shared memory; every other a' goes back in place tagged
+//          L2::evict_last.  One flag per tile (plain store) says which of the two happened.
 // barrier  only the CONSUMERS rendezvous (named barrier + one atomic per CTA).  The producers do not: p, m, v do
-//          not depend on the clip scale, so as soon as pass 1 is issued and its slots are drained they start
-//          streaming pass 2's tiles into the ring -- HBM stays busy while the CTAs wait for each other.
-// pass 2   ring slot = [p | m | v] (24 KB, kP2Slots per group); L2-resident tiles youngest first, then the
-//          Tensor-Memory tiles: clip, AdamWeightDecay/Adam, STG p, m, v, a = 0.
+//          not depend on the clip scale, so they start streaming the group's own Tensor-Memory tiles into the
+//          ring as soon as pass 1 is drained -- HBM stays busy while the CTAs wait for each other.
+// pass 2   ring slot = [p | m | v | a'] (32 KB).  First the group's own Tensor-Memory tiles, then tickets over
+//          all tiles, youngest first (a' still in L2), skipping the parked ones: clip, AdamWeightDecay/Adam,
+//          STG p, m, v, a = 0.
 // Tiles that bulk copies cannot move (gradient / parameter pointer not 16-byte aligned, or shorter than one
 // float4) go through the same full/empty protocol with nothing copied and are loaded by the consumers with
-// scalar LDGs; producer and consumers evaluate the same predicates (bulk_vecs / aligned16(p)).
+// scalar LDGs; producer and consumers evaluate the same predicates (bulk_vecs / bulk_vecs2).
+// Per-launch counters (tickets, pool length, accumulator) exist twice; launch k uses set k & 1 and clears the
+// other one, k being read off the monotonic barrier counter -- no host-side state, so launches replay in CUDA graphs.
 // =============================================================================================
 constexpr int kGroups = 3;                        // consumer groups per CTA
 constexpr int kConsumerThreads = kThreads * kGroups;        // 768
@@ -397,13 +405,23 @@ constexpr int kRingVecs = kP1Slots * kP1SlotVecs; // per group
 constexpr int kP2Slots = kRingVecs / kP2SlotVecs; // 4 x 16 KB = 64 KB -> 2 x 32 KB
 constexpr int kRingBytes = kGroups * kRingVecs * 16;   // dynamic shared memory of the kernel (192 KB)
 static_assert(kP2Slots >= 1 && kP1Slots <= 8, "ring must hold at least one [p|m|v|a'] slot");
-// what the producer tells the consumers about the tile it put into a pass-2 slot
-struct __align__(16) SlotMeta {
-  TileDesc d;          // len == 0: end of pass 2
-  uint32_t tmem_slot;  // a' is parked in this Tensor-Memory slot of the group (kNoTmem: it is in the slot's 4th quarter / in global memory)
-  uint32_t pad[3];
-};
 constexpr int kMaxSlots = 8;
+constexpr int kTicketBatch = 4;                   // pass-1 tickets a producer draws at once while plenty of tiles are left
+// what the producer tells the consumers about the tile it put into a slot
+struct __align__(16) SlotMeta {
+  TileDesc d;          // len == 0: end of the pass
+  uint32_t tile;       // index into the tile table
+  uint32_t tmem_slot;  // pass 2: a' is parked in this Tensor-Memory slot of the group (kNoTmem: it is in the slot's 4th quarter / in global memory)
+  uint32_t pad[2];
+};
+// exact accumulation of non-negative doubles: 68 bins of 32 payload bits in 64-bit containers cover the whole
+// binary64 range (2^-1074 .. 2^1024); a container overflows only after 2^31 additions
+constexpr int kAccBins = 68;
+struct LaunchCounters {
+  unsigned long long p1_ticket, p2_ticket;
+  unsigned int nonfinite, pad;                  // nonfinite: bit 0 = +inf seen, bit 1 = NaN seen
+  unsigned long long bins[kAccBins];
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -494,18 +512,62 @@ __device__ __forceinline__ bool tmem_ok(const TileDesc& d, const KernelParams<CA
   return ok;
 }
 
-// one producer lane's view of a ring: slot index + how often the ring has wrapped
+// one thread's view of a ring: slot index + how often the ring has wrapped
 struct RingPos {
   int slot = 0;
   uint32_t use = 0;
   __device__ __forceinline__ void advance(int nslots) { if (++slot == nslots) { slot = 0; ++use; } }
 };
 
-// ---- pass 1, consumer side: one tile out of slot [G | a] -------------------------------------------------
+// ---- exact accumulator ---------------------------------------------------------------------------------------
+// add the non-negative double w to `bins` exactly; non-finite values only raise a flag.  `bins` is PRIVATE to the
+// calling thread (one accumulator per warp, lane 0 owns it): plain read-modify-write, no atomics, no contention
+__device__ __forceinline__ void acc_add(unsigned long long* bins, unsigned int& nonfinite, const double w) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(w);
+  const unsigned int e = (unsigned int)(bits >> 52) & 0x7ffu;
+  if (e == 0x7ffu) { nonfinite |= (bits & 0x000fffffffffffffull) ? 2u : 1u; return; }
+  unsigned long long mant = bits & 0x000fffffffffffffull;
+  if (e != 0) mant |= 1ull << 52;
+  if (mant == 0) return;
+  const unsigned int pos = e ? e - 1u : 0u;           // bit position of mant's LSB: value = mant * 2^(pos - 1074)
+  const unsigned int q = pos >> 5, r = pos & 31u;
+  const unsigned long long lo = mant << r;            // r <= 31, mant < 2^53: the 85-bit product is split by hand
+  const unsigned long long hi = r ? (mant >> (64u - r)) : 0ull;
+  bins[q] += lo & 0xffffffffull;
+  bins[q + 1] += lo >> 32;
+  bins[q + 2] += hi;
+}
+// the accumulated value as a double (deterministic: carries are propagated low to high, the three leading 32-bit
+// digits are combined in a fixed order; relative error <= 2^-52); executed by one thread
+__device__ __forceinline__ double acc_value(const unsigned long long* bins /* kAccBins */, const unsigned int nonfinite) {
+  if (nonfinite & 2u) return __longlong_as_double(0x7ff8000000000000ll);
+  if (nonfinite & 1u) return __longlong_as_double(0x7ff0000000000000ll);
+  unsigned long long carry = 0;
+  int top = -1;
+  for (int i = 0; i < kAccBins; ++i) {
+    const unsigned long long t = bins[i] + carry;
+    carry = t >> 32;
+    if (t & 0xffffffffull) top = i;
+  }
+  if (top < 0) return 0.0;
+  carry = 0;
+  unsigned int g0 = 0, g1 = 0, g2 = 0;                 // digits top-2, top-1, top
+  for (int i = 0; i <= top; ++i) {
+    const unsigned long long t = bins[i] + carry;
+    const unsigned int digit = (unsigned int)(t & 0xffffffffull);
+    carry = t >> 32;
+    if (i == top - 2) g0 = digit;
+    if (i == top - 1) g1 = digit;
+    if (i == top) g2 = digit;
+  }
+  const double m = ((double)g2 * 4294967296.0 + (double)g1) * 4294967296.0 + (double)g0;
+  return scalbn(m, 32 * (top - 2) - 1074);
+}
+
+// ---- pass 1, consumer side: one tile out of slot [G | a]; returns this THREAD's partial of sum((a'/N)^2) ----
 template <bool HAS_G, int CAP>
-__device__ __forceinline__ float norm_tile(const TileDesc& d, const KernelParams<CAP>& prm, const float4* slot,
-                                           uint64_t* full, uint64_t* empty, const uint32_t parity,
-                                           const uint32_t tmem, const uint64_t pol, long long& dbg_wait) {
+__device__ __forceinline__ float norm_tile(const TileDesc& d, const KernelParams<CAP>& prm, const float4* slot, uint64_t* empty,
+                                           const uint32_t tmem, const uint64_t pol) {
   const float* __restrict__ g = nullptr;
   if constexpr (HAS_G) g = grad_ptr(prm.tab, d);
   float* __restrict__ a = prm.accum + (size_t)d.soff32 * kSlabAlign;
@@ -513,13 +575,6 @@ __device__ __forceinline__ float norm_tile(const TileDesc& d, const KernelParams
   const float nf = prm.sc.nf, inv_nf = prm.sc.inv_nf;
   const uint32_t nvec = bulk_vecs(d, g);
   float acc = 0.f;
-#ifdef GACCUM_EXPERIMENTS
-  const long long t_w0 = clock64();
-#endif
-  mbar_wait(full, parity);                      // G and a have landed (or the producer had nothing to copy)
-#ifdef GACCUM_EXPERIMENTS
-  dbg_wait += clock64() - t_w0;
-#endif
   if (nvec > 0) {
     float4* a4 = reinterpret_cast<float4*>(a);
     float4 x[kUnroll], gg[kUnroll];
@@ -628,39 +683,26 @@ __device__ __forceinline__ void update_tile2(const TileDesc& d, const KernelPara
   }
 }
 
-// Deterministic reduction over the 768 consumer threads (the producers do not take part): total in thread 0.
-__device__ __forceinline__ double consumer_reduce_to_double(double x, double* smem /* 24 */) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) smem[warp] = x;
-  named_bar_sync(1, kConsumerThreads);
-  double tot = 0.0;
-  if (threadIdx.x == 0)
-    for (int w = 0; w < kConsumerThreads / 32; ++w) tot += smem[w];
-  return tot;
-}
-
-// Dynamic shared memory of apply_clip_kernel: 3 groups x kRingVecs float4 (144 KB).
+// Dynamic shared memory of apply_clip_kernel: 3 groups x kRingVecs float4 (192 KB).
 template <int VARIANT, bool HAS_G, int CAP>
 __global__ void __launch_bounds__(kClipThreads, 1)
 apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
   extern __shared__ __align__(128) unsigned char smem_dyn[];
-  __shared__ double red[kConsumerThreads / 32];
+  __shared__ unsigned long long s_bins[kConsumerThreads / 32][kAccBins];   // one exact accumulator per consumer warp (13 KB)
+  __shared__ unsigned int s_nonfinite;
   __shared__ float s_bcast[2];
-  __shared__ uint32_t s_tmem_base;
+  __shared__ uint32_t s_tmem_base, s_set;
   __shared__ __align__(8) uint64_t s_full1[kGroups][kMaxSlots], s_empty1[kGroups][kMaxSlots];
   __shared__ __align__(8) uint64_t s_full2[kGroups][kMaxSlots], s_empty2[kGroups][kMaxSlots];
-  __shared__ __align__(8) uint64_t s_go[kGroups];
-  __shared__ SlotMeta s_meta[kGroups][kMaxSlots];
+  __shared__ __align__(8) uint64_t s_go[kGroups], s_p1done[kGroups];
+  __shared__ SlotMeta s_meta1[kGroups][kMaxSlots], s_meta2[kGroups][kMaxSlots];
+  __shared__ SlotMeta s_own[kGroups][kTmemTiles];          // tiles whose a' this group parked in Tensor Memory
+  __shared__ int s_nown[kGroups];
 
   const int warp = (int)threadIdx.x >> 5;
   const bool is_producer = warp >= kConsumerThreads / 32;
   const int grp = is_producer ? warp - kConsumerThreads / 32 : (int)threadIdx.x / kThreads;   // group served / group id
   const int nt = prm.num_tiles, G = (int)gridDim.x * kGroups;
-  const int b = (int)blockIdx.x * kGroups + grp;                   // virtual block id
-  const int C = b < nt ? (nt - 1 - b) / G + 1 : 0;                 // tiles of this group
-  const int n_tm = min(prm.tmem_tiles, C);                         // tiles j < n_tm park a' in Tensor Memory
   float4* const ring = reinterpret_cast<float4*>(smem_dyn) + (size_t)grp * kRingVecs;
   const uint64_t pol_last = policy_evict_last();
 
@@ -677,22 +719,33 @@ apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
 #endif
   stamp(0);
 
-  // ---- set-up: mbarriers, Tensor Memory ---------------------------------------------------------------
+  // ---- set-up: which counter set this launch uses, mbarriers, accumulator, Tensor Memory ---------------------
   if (threadIdx.x == 0) {
+    // every CTA that has not yet arrived at this launch's barrier reads a value in [k*grid, (k+1)*grid)
+    const unsigned long long k = ld_acquire_gpu_u64(prm.barrier) / gridDim.x;
+    s_set = (uint32_t)(k & 1ull);
+    s_nonfinite = 0;
 #pragma unroll
     for (int g = 0; g < kGroups; ++g) {
       for (int sl = 0; sl < kP1Slots; ++sl) { mbar_init(&s_full1[g][sl], 1); mbar_init(&s_empty1[g][sl], kThreads / 32); }
       for (int sl = 0; sl < kP2Slots; ++sl) { mbar_init(&s_full2[g][sl], 1); mbar_init(&s_empty2[g][sl], kThreads / 32); }
-      mbar_init(&s_go[g], 1);
+      mbar_init(&s_go[g], 1); mbar_init(&s_p1done[g], 1);
+      s_nown[g] = 0;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  for (int i = threadIdx.x; i < (kConsumerThreads / 32) * kAccBins; i += kClipThreads) (&s_bins[0][0])[i] = 0ull;
   if (prm.tmem_tiles > 0 && warp == 1) tmem_alloc(&s_tmem_base);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = prm.tmem_tiles > 0 ? s_tmem_base : 0u;
+  LaunchCounters* const ctr = prm.counters + s_set;
+  if (blockIdx.x == 0 && threadIdx.x >= 64 && threadIdx.x < 64 + (int)(sizeof(LaunchCounters) / 8)) {
+    // the other set was used by the previous launch on this plan, which is complete: clear it for the next one
+    reinterpret_cast<unsigned long long*>(prm.counters + (s_set ^ 1u))[threadIdx.x - 64] = 0ull;
+  }
 
   if (is_producer) {
     // =========================== producer warp of group `grp` ===========================
@@ -702,24 +755,34 @@ apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
     long long dbg_empty = 0;
     const long long dbg_p0 = clock64();
 #endif
-    // ---- pass 1: [G | a] of tiles j = 0..C-1.  Descriptors are fetched 32 at a time, one per lane ----
+    // ---- pass 1: tickets over all tiles, kTicketBatch at a time while plenty are left (one atomic per lane, the
+    //      descriptor loads of a batch overlap), single tickets near the end so that no SM is left holding a batch ----
     {
-      auto fetch = [&](int j0, TileDesc& d) { const int j = j0 + lane; if (j < C) d = prm.tiles[b + j * G]; };
-      TileDesc dc{}, dn{};
-      fetch(0, dc); fetch(32, dn);
       RingPos rp;
-      for (int j0 = 0; j0 < C; j0 += 32) {
-        const int nb = min(32, C - j0);
-        for (int l = 0; l < nb; ++l) {
-          TileDesc d;
-          d.tensor_flags = __shfl_sync(0xffffffffu, dc.tensor_flags, l);
-          d.len = __shfl_sync(0xffffffffu, dc.len, l);
-          d.toff = __shfl_sync(0xffffffffu, dc.toff, l);
-          d.soff32 = __shfl_sync(0xffffffffu, dc.soff32, l);
+      bool done = false;
+      unsigned long long last = 0;
+      while (!done) {
+        const long long left = (long long)nt - (long long)last;
+        const int batch = left > 8ll * G ? kTicketBatch : (left > 2ll * G ? 2 : 1);
+        unsigned long long tk = ~0ull;
+        TileDesc d{};
+        if (lane < batch) {
+          tk = atomicAdd(&ctr->p1_ticket, 1ull);
+          if (tk < (unsigned long long)nt) d = prm.tiles[tk];
+        }
+        for (int l = 0; l < batch; ++l) {
+          const unsigned long long tkl = __shfl_sync(0xffffffffu, tk, l);
+          if (tkl >= (unsigned long long)nt) { done = true; continue; }      // lanes get their tickets in no particular order:
+          last = tkl;                                                        // a valid one may follow an exhausted one
+          TileDesc dl;
+          dl.tensor_flags = __shfl_sync(0xffffffffu, d.tensor_flags, l);
+          dl.len = __shfl_sync(0xffffffffu, d.len, l);
+          dl.toff = __shfl_sync(0xffffffffu, d.toff, l);
+          dl.soff32 = __shfl_sync(0xffffffffu, d.soff32, l);
           if (lane == 0) {
             const float* g = nullptr;
-            if constexpr (HAS_G) g = grad_ptr(prm.tab, d);
-            const uint32_t nvec = bulk_vecs(d, g);
+            if constexpr (HAS_G) g = grad_ptr(prm.tab, dl);
+            const uint32_t nvec = bulk_vecs(dl, g);
             uint64_t* full = &s_full1[grp][rp.slot];
 #ifdef GACCUM_EXPERIMENTS
             const long long t_e0 = clock64();
@@ -728,23 +791,28 @@ apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
 #ifdef GACCUM_EXPERIMENTS
             dbg_empty += clock64() - t_e0;
 #endif
+            SlotMeta* meta = &s_meta1[grp][rp.slot];
+            meta->d = dl;
+            meta->tile = (uint32_t)tkl;
             if (nvec > 0) {
               float4* dst = ring + (size_t)rp.slot * kP1SlotVecs;
               mbar_arrive_expect_tx(full, nvec * 16u * (g ? 2u : 1u));
               if (g) bulk_g2s(dst, g, nvec * 16u, full, pol_first);
-              bulk_g2s(dst + kTile / 4, prm.accum + (size_t)d.soff32 * kSlabAlign, nvec * 16u, full, pol_first);
+              bulk_g2s(dst + kTile / 4, prm.accum + (size_t)dl.soff32 * kSlabAlign, nvec * 16u, full, pol_first);
             } else {
               mbar_arrive(full);                                             // nothing to copy: complete the phase
             }
           }
           rp.advance(kP1Slots);
         }
-        dc = dn;
-        fetch(j0 + 64, dn);
       }
-      // drain: pass 2's slots overlay pass 1's, so every pass-1 slot must have been released for the last time
       if (lane == 0) {
+        // end marker, then drain: pass 2's slots overlay pass 1's, so every slot must have been released for the last time
+        mbar_wait(&s_empty1[grp][rp.slot], (rp.use & 1u) ^ 1u);
+        s_meta1[grp][rp.slot].d.len = 0;
+        mbar_arrive(&s_full1[grp][rp.slot]);
         for (int sl = 0; sl < kP1Slots; ++sl) {
+          if (sl == rp.slot) continue;
           const uint32_t n = rp.use + (sl < rp.slot ? 1u : 0u);              // times slot sl was armed
           if (n > 0) mbar_wait(&s_empty1[grp][sl], (n - 1u) & 1u);
         }
@@ -759,47 +827,42 @@ apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
 #endif
     // ---- pass 2.  First the group's own Tensor-Memory tiles (their a' cannot move; their p, m, v do not depend on
     //      the clip scale, so these copies start BEFORE the grid barrier and HBM stays busy while the CTAs wait for
-    //      each other).  Then tiles out of the GLOBAL POOL of L2-resident tiles, youngest first, one atomic ticket per
-    //      tile: SMs that get a larger share of the saturated memory system simply take more tickets, so all SMs
-    //      finish together (with static tiles the slowest SM finished 40 us after the fastest).  Pool tiles carry
-    //      their a' in the slot's 4th quarter; they may only be fetched once every CTA has passed the barrier. ----
+    //      each other).  Then tickets over the pool of L2-resident tiles, youngest first.  Pool tiles carry their a'
+    //      in the slot's 4th quarter; they may only be fetched once every CTA has passed the barrier. ----
     if (lane == 0) {
       RingPos rp;
-      const int pool_lo = prm.tmem_tiles * G;                                   // tiles [pool_lo, nt) form the pool
-      const unsigned long long pool_n = (unsigned long long)max(0, nt - pool_lo);
-      const unsigned long long draws = pool_n + (unsigned long long)G;          // per launch: every producer over-draws exactly once
-      int jb = 0;                                                               // next own Tensor-Memory tile
+      mbar_wait(&s_p1done[grp], 0);             // the group's leader has recorded its last parked tile
+      const int n_own = s_nown[grp];
+      int jb = 0;
       bool past_barrier = false;
       while (true) {
-        int tile;
+        TileDesc d;
         uint32_t tmem_slot = kNoTmem;
-        auto wait_for_barrier = [&]() {
+        if (jb < n_own) {
+          d = s_own[grp][jb].d;
+          tmem_slot = (uint32_t)jb;
+          ++jb;
+        } else {
           if (!past_barrier) {
             mbar_wait(&s_go[grp], 0);                                           // the consumers are through the grid barrier
             asm volatile("fence.proxy.async;" ::: "memory");                    // generic-proxy a' stores -> our bulk reads
             past_barrier = true;
           }
-        };
-        if (jb < n_tm) {
-          tile = b + jb * G;
-          tmem_slot = (uint32_t)jb;
-          ++jb;
-        } else {
-          wait_for_barrier();
-          const unsigned long long tk = atomicAdd(prm.pool_ticket, 1ull) % draws;
-          if (tk >= pool_n) break;
-          tile = nt - 1 - (int)tk;                                              // youngest a' lines first
+          const unsigned long long tk = atomicAdd(&ctr->p2_ticket, 1ull);
+          if (tk >= (unsigned long long)nt) break;
+          const int tile = nt - 1 - (int)tk;                                    // youngest a' lines first
+          const uint32_t is_parked = __ldcg(prm.parked + tile);                 // (both loads depend on the ticket only: they overlap)
+          d = prm.tiles[tile];
+          if (is_parked) continue;                                              // its owner updates it from Tensor Memory
         }
-        const TileDesc d = prm.tiles[tile];
         const float* p = param_ptr(prm.tab, d);
         const uint32_t nvec = bulk_vecs2(d, p);
-        const bool in_tmem = tmem_slot != kNoTmem && tmem_ok<HAS_G>(d, prm);
-        if (!in_tmem) wait_for_barrier();                                       // a' of this tile is in global memory: complete only after pass 1
+        const bool in_tmem = tmem_slot != kNoTmem;
         uint64_t* full = &s_full2[grp][rp.slot];
         mbar_wait(&s_empty2[grp][rp.slot], (rp.use & 1u) ^ 1u);
-        SlotMeta* meta = &s_meta[grp][rp.slot];
+        SlotMeta* meta = &s_meta2[grp][rp.slot];
         meta->d = d;
-        meta->tmem_slot = in_tmem ? tmem_slot : kNoTmem;
+        meta->tmem_slot = tmem_slot;
         if (nvec > 0) {
           const size_t soff = (size_t)d.soff32 * kSlabAlign;
           float4* dst = ring + (size_t)rp.slot * kP2SlotVecs;
@@ -813,65 +876,91 @@ apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
         }
         rp.advance(kP2Slots);
       }
-      // end marker
-      mbar_wait(&s_empty2[grp][rp.slot], (rp.use & 1u) ^ 1u);
-      s_meta[grp][rp.slot].d.len = 0;
+      mbar_wait(&s_empty2[grp][rp.slot], (rp.use & 1u) ^ 1u);                   // end marker
+      s_meta2[grp][rp.slot].d.len = 0;
       mbar_arrive(&s_full2[grp][rp.slot]);
     }
     __syncwarp();
   } else {
     // =========================== consumer group ===========================
-    double acc = 0.0;
-    long long dbg_wait = 0;
 #ifdef GACCUM_EXPERIMENTS
+    long long dbg_wait = 0;
     const long long dbg_t0 = clock64();
 #endif
-    if (C > 0) {
-      // ---- pass 1 ----
-      TileDesc d = prm.tiles[b];
+    const bool leader = (threadIdx.x & (kThreads - 1)) == 0;
+    // ---- pass 1: whatever tiles the producer hands over, until its end marker ----
+    unsigned int my_nonfinite = 0;
+    {
       RingPos rp;
-      for (int j = 0; j < C; ++j) {
-        TileDesc dnx = d;
-        if (j + 1 < C) dnx = prm.tiles[b + (j + 1) * G];          // next descriptor: off the critical path
-        const uint32_t tm = (j < n_tm && tmem_ok<HAS_G>(d, prm)) ? tmem_slot_addr(tmem_base, j) : kNoTmem;
-        acc += (double)norm_tile<HAS_G>(d, prm, ring + (size_t)rp.slot * kP1SlotVecs, &s_full1[grp][rp.slot], &s_empty1[grp][rp.slot],
-                                        rp.use & 1u, tm, pol_last, dbg_wait);
+      int n_parked = 0;
+      while (true) {
+#ifdef GACCUM_EXPERIMENTS
+        const long long t_w0 = clock64();
+#endif
+        mbar_wait(&s_full1[grp][rp.slot], rp.use & 1u);
+#ifdef GACCUM_EXPERIMENTS
+        dbg_wait += clock64() - t_w0;
+#endif
+        const SlotMeta meta = s_meta1[grp][rp.slot];
+        if (meta.d.len == 0) break;
+        // Tensor Memory takes the first kTmemTiles FULL, vector-path tiles this group sees (tcgen05.st/ld are warp-collective)
+        const bool park = n_parked < prm.tmem_tiles && tmem_ok<HAS_G>(meta.d, prm);
+        const uint32_t tm = park ? tmem_slot_addr(tmem_base, n_parked) : kNoTmem;
+        const float part = norm_tile<HAS_G>(meta.d, prm, ring + (size_t)rp.slot * kP1SlotVecs, &s_empty1[grp][rp.slot], tm, pol_last);
+        // warp total in fp64, fixed butterfly order; lane 0 adds it EXACTLY into the CTA's accumulator
+        double w = (double)part;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+        if ((threadIdx.x & 31) == 0) acc_add(s_bins[warp], my_nonfinite, w);
+        if (leader) {
+          if (park) {
+            s_own[grp][n_parked] = meta;                      // remembered for pass 2 (this group's producer reads it after pass 1)
+            s_nown[grp] = n_parked + 1;
+          }
+          prm.parked[meta.tile] = park ? 1u : 0u;             // 0: any SM may update this tile in pass 2 (plain store, nobody waits for it)
+        }
+        n_parked += park ? 1 : 0;
         rp.advance(kP1Slots);
-        d = dnx;
       }
     }
 #ifdef GACCUM_EXPERIMENTS
-    if (prm.debug && (threadIdx.x & (kThreads - 1)) == 0) {
+    if (prm.debug && leader) {
       prm.debug[blockIdx.x * 16 + 4 + grp] = (unsigned long long)dbg_wait;                 // cycles waiting for G | a
       prm.debug[blockIdx.x * 16 + 10 + grp] = (unsigned long long)(clock64() - dbg_t0);   // cycles of the group's pass 1
     }
 #endif
-    const double part = consumer_reduce_to_double(acc, red);
+    if (leader) mbar_arrive(&s_p1done[grp]);                 // s_own / s_nown of this group are final
+    named_bar_sync(1, kConsumerThreads);                     // every consumer thread of this CTA is through pass 1
+    // flush this CTA's accumulators into the launch's global one (integer adds: order does not matter)
+    if (my_nonfinite) atomicOr(&s_nonfinite, my_nonfinite);
+    if (threadIdx.x < kAccBins) {
+      unsigned long long v = 0;
+      for (int w = 0; w < kConsumerThreads / 32; ++w) v += s_bins[w][threadIdx.x];
+      if (v) atomicAdd(&ctr->bins[threadIdx.x], v);
+    }
+    named_bar_sync(1, kConsumerThreads);
+    if (threadIdx.x == 0 && s_nonfinite) atomicOr(&ctr->nonfinite, s_nonfinite);
     stamp(1);
     // ---- grid barrier of the consumers: one atomic per CTA on a monotonic counter (every launch of this plan
     //      uses the same grid, so the counter advances by gridDim.x per launch); cooperative launch guarantees
     //      that all CTAs are co-resident ----
     if (threadIdx.x == 0) {
-      prm.partials[blockIdx.x] = part;
       __threadfence();
       const unsigned long long old = atomicAdd(prm.barrier, 1ull);
       const unsigned long long target = (old / gridDim.x + 1ull) * gridDim.x;
       while (ld_acquire_gpu_u64(prm.barrier) < target) { __nanosleep(20); }
     }
     named_bar_sync(1, kConsumerThreads);
-    if ((threadIdx.x & (kThreads - 1)) == 0) mbar_arrive(&s_go[grp]);    // this group's producer may now fetch pool tiles
+    if (leader) mbar_arrive(&s_go[grp]);                     // this group's producer may now fetch pool tiles
     stamp(2);
-    // ---- every CTA combines the per-CTA partials in the same fixed order ---------------------------
-    if (threadIdx.x < 32) {
-      double tot = 0.0;
-      for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) tot += __ldcg(prm.partials + i);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-      if (threadIdx.x == 0) {
-        const float g_norm = __fsqrt_rn((float)tot);        // tf.linalg.global_norm
-        s_bcast[0] = clip_scale(g_norm, prm.sc.clip);
-        s_bcast[1] = g_norm;
-      }
+    // ---- every CTA evaluates the same exact sum the same way: bit-identical gn and clip scale everywhere ----
+    if (threadIdx.x < kAccBins) s_bins[0][threadIdx.x] = __ldcg(&ctr->bins[threadIdx.x]);
+    named_bar_sync(1, kConsumerThreads);
+    if (threadIdx.x == 0) {
+      const double tot = acc_value(s_bins[0], __ldcg(&ctr->nonfinite));
+      const float g_norm = __fsqrt_rn((float)tot);          // tf.linalg.global_norm
+      s_bcast[0] = clip_scale(g_norm, prm.sc.clip);
+      s_bcast[1] = g_norm;
     }
     named_bar_sync(1, kConsumerThreads);
     const float s = s_bcast[0];
@@ -880,7 +969,7 @@ apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
       RingPos rp;
       while (true) {
         mbar_wait(&s_full2[grp][rp.slot], rp.use & 1u);
-        const SlotMeta meta = s_meta[grp][rp.slot];
+        const SlotMeta meta = s_meta2[grp][rp.slot];
         if (meta.d.len == 0) break;
         const uint32_t tm = meta.tmem_slot != kNoTmem ? tmem_slot_addr(tmem_base, (int)meta.tmem_slot) : kNoTmem;
         update_tile2<VARIANT>(meta.d, prm, s, ring + (size_t)rp.slot * kP2SlotVecs, &s_empty2[grp][rp.slot], tm);

@@ -32,6 +32,24 @@ class DataParallelTrainOp:
         self.world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         self.allreduces = 0
 
+    def state_dict(self):
+        """Replicated moments are already complete on every rank; the rank-local accumulators are summed (04:55)."""
+        e = self.engine
+        if self.world == 1:
+            return e.state_dict()
+        acc = e.accum.clone()
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=self.group)
+        saved, e.accum = e.accum, acc
+        try:
+            return e.state_dict()
+        finally:
+            e.accum = saved
+
+    def load_state_dict(self, sd, strict: bool = True) -> None:
+        self.engine.load_state_dict(sd, strict)
+        if self.world > 1 and dist.get_rank(self.group) != 0:
+            self.engine.accum.zero_()
+
     def run(self, grads: Sequence[Optional[torch.Tensor]]) -> bool:
         e = self.engine
         if self.world == 1:
@@ -139,6 +157,33 @@ class FusedDataParallelTrainOp:
         self.exchanges += 1
         e._after(True, lr)
         return True
+
+    # -- checkpoint compatibility under data parallelism (reference 04:55 aggregation=SUM) --------
+    def state_dict(self):
+        """What the reference's Saver would hold: full adam_m / adam_v (every rank's owned shard gathered) and the
+        SUM over ranks of the rank-local accumulators (04:55 declares them aggregation=SUM).  Collective: every rank
+        must call it; every rank gets the same dictionary."""
+        e = self.engine
+        full = self.gather_state()
+        acc = e.accum.clone()
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=self.group)
+        saved = (e.m, e.v, e.accum)
+        e.m, e.v, e.accum = full["m"], full["v"], acc
+        try:
+            return e.state_dict()
+        finally:
+            e.m, e.v, e.accum = saved
+
+    def load_state_dict(self, sd, strict: bool = True) -> None:
+        """Inverse of state_dict(): every rank takes parameters and the full moments (only its shard is ever used);
+        the summed accumulators go to rank 0 alone, the others start the rest of the window from zero, so the next
+        exchange reproduces the checkpointed sum."""
+        e = self.engine
+        e.load_state_dict(sd, strict)
+        if self.rank != 0:
+            e.accum.zero_()
+        torch.cuda.synchronize(e.device)
+        dist.barrier(group=self.group)
 
     def gather_state(self):
         """Full m and v slabs (every rank's owned range all-gathered) for checkpointing."""

@@ -98,17 +98,20 @@ class Estimator:
         path = self._ckpt_path()
         if path and os.path.exists(path) and self._spec.train_op is not None:
             sd = torch.load(path, map_location="cpu")
-            eng = self._spec.train_op.engine
-            eng.load_state_dict({k: v.to(eng.device) if torch.is_tensor(v) and v.dim() else v for k, v in sd.items()})
-            graph.get_or_create_global_step().assign(int(sd["global_step"]))
+            op = self._spec.train_op
+            op.load_state_dict({k: v.to(op.engine.device) if torch.is_tensor(v) and v.dim() else v for k, v in sd.items()})
 
     def save_checkpoint(self) -> Optional[str]:
         path = self._ckpt_path()
         if path and self._spec is not None and self._spec.train_op is not None:
-            os.makedirs(self.config.model_dir, exist_ok=True)
-            eng = self._spec.train_op.engine
-            eng.global_step = int(graph.get_or_create_global_step())
-            torch.save({k: (v.cpu() if torch.is_tensor(v) else v) for k, v in eng.state_dict().items()}, path)
+            import torch.distributed as dist
+            sd = self._spec.train_op.state_dict()          # collective under data parallelism: full moments, summed accumulators
+            multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+            if not multi or dist.get_rank() == 0:          # one writer (04: the chief saves)
+                os.makedirs(self.config.model_dir, exist_ok=True)
+                torch.save({k: (v.cpu() if torch.is_tensor(v) else v) for k, v in sd.items()}, path)
+            if multi:
+                dist.barrier()
         return path
 
     # -- the loops --------------------------------------------------------------------------------

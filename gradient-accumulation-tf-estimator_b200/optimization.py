@@ -169,6 +169,15 @@ class TrainOp:
     def accum_n(self) -> int:
         return self.engine.N
 
+    def state_dict(self):
+        """Checkpoint under the reference's variable names; correct under data parallelism (collective there)."""
+        self.engine.global_step = int(self.global_step)
+        return self.dp.state_dict() if self.dp is not None else self.engine.state_dict()
+
+    def load_state_dict(self, sd, strict: bool = True) -> None:
+        (self.dp if self.dp is not None else self.engine).load_state_dict(sd, strict)
+        self.global_step.assign(int(sd["global_step"]))
+
     def gradients(self) -> List[Optional[torch.Tensor]]:
         """``tf.gradients(loss, tvars)`` (optimization.py:71): evaluated every micro-step."""
         loss = self.loss() if callable(self.loss) else self.loss

@@ -11,6 +11,7 @@ in csrc/.
 from __future__ import annotations
 
 import ctypes as C
+import re
 from typing import Callable, Dict, List, Optional, Sequence
 
 import numpy as np
@@ -41,7 +42,8 @@ class GaccumTrainOp:
                 raise ValueError("parameters must be contiguous fp32 tensors on one device")
         self.device = dev
         self.params = list(params)
-        self.names = [n for n in names]
+        # optimization.py:135-143 names slots after _get_variable_name(param.name): the ":0" tensor suffix is stripped
+        self.names = [re.sub(r":\d+$", "", n) for n in names]
         self.hp = hp
         self.N = int(accum_n)
         self.lr_fn = lr_fn
@@ -244,6 +246,90 @@ class GaccumTrainOp:
         if self.hp.variant == ADAM and "beta1_power" in sd:
             self.beta1_power = float(sd["beta1_power"])
             self.beta2_power = float(sd["beta2_power"])
+
+
+class PackedTrainOp:
+    """SURVEY.md 8(f) #2 -- gradient hand-off without the scatter.
+
+    The reference keeps T parameters, T gradients and T ``accum_grads`` as separate tensors
+    (optimization.py:70-71, 78) and adds gradient to accumulator with T ``assign_add`` ops per micro-step (:81, 93).
+    Here the parameters are re-pointed at views of ONE flat slab in the plan's layout and every ``p.grad`` is a view
+    of the packed accumulator slab, so the producer (autograd's ``AccumulateGrad``: ``grad += new_grad``, one fp32
+    rounding per micro-step -- the same arithmetic as ``assign_add``) accumulates IN PLACE, straight into ``accum``:
+      * accumulate micro-steps launch nothing from this library (12 -> 0 B/param of train_op traffic),
+      * the apply micro-step runs the slab-to-slab kernel with no gradient stream and no pointer table
+        (``gaccum_step_packed(grad_slab=NULL)``: 32 B/param instead of 36) and leaves ``accum`` == ``p.grad`` zeroed
+        for the next window.
+    Call ``step()`` once per micro-step, after ``loss.backward()``.  Never set the gradients to ``None``
+    (``zero_grad(set_to_none=True)``) -- the views are the accumulator.
+    """
+
+    def __init__(self, params: Sequence[torch.Tensor], names: Sequence[str], hp: HParams, accum_n: int,
+                 lr_fn: Callable[[int], float],
+                 exclude_from_weight_decay: Optional[Sequence[str]] = ("LayerNorm", "layer_norm", "bias"),
+                 global_step: int = 0):
+        if not params:
+            raise ValueError("no trainable variables")
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise _lib.GaccumError(_lib.ENODEVICE, "parameters must live on a CUDA device: the train_op has no CPU fallback")
+        self.device, self.params, self.names = dev, list(params), list(names)
+        self.hp, self.N, self.lr_fn, self.global_step = hp, int(accum_n), lr_fn, int(global_step)
+        self.decay = _lib.decay_mask(self.names, hp.weight_decay_rate, exclude_from_weight_decay) \
+            if hp.variant == _lib.ADAM_WEIGHT_DECAY else [False] * len(params)
+        self.plan = Plan([p.numel() for p in params], self.decay, hp, device=dev.index or 0)
+        n = max(self.plan.padded_size, 32)
+        self.param_slab = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.accum = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(n, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, o in zip(self.params, self.plan.offsets):
+                if p.dtype != torch.float32:
+                    raise ValueError("parameters must be fp32")
+                view = self.param_slab[o:o + p.numel()].view(p.shape)
+                view.copy_(p)
+                p.data = view                                            # the caller's tensors now alias the slab
+                p.grad = self.accum[o:o + p.numel()].view(p.shape)      # autograd accumulates straight into accum_grads
+        self.beta1_power, self.beta2_power = _f32(hp.beta1), _f32(hp.beta2)
+        self._stats_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+        self.launches = 0
+
+    def _view(self, slab, i):
+        o = self.plan.offsets[i]
+        return slab[o:o + self.params[i].numel()].view(self.params[i].shape)
+
+    def accum_view(self, i): return self._view(self.accum, i)
+    def m_view(self, i): return self._view(self.m, i)
+    def v_view(self, i): return self._view(self.v, i)
+
+    def step(self, stream: Optional[int] = None) -> bool:
+        """One ``session.run(train_op)`` AFTER the backward pass has added this micro-batch's gradient into
+        ``p.grad`` (== accum).  Returns True if it applied (optimization.py:91, pre-increment predicate)."""
+        g = self.global_step
+        applied = _lib.is_apply_step(g, self.N)
+        if applied:
+            for p, o in zip(self.params, self.plan.offsets):     # a caller that dropped the views broke the contract
+                if p.grad is None or p.grad.data_ptr() != self.accum.data_ptr() + 4 * o:
+                    raise RuntimeError("p.grad no longer aliases the packed accumulator (zero_grad(set_to_none=True)?)")
+            lr = self.lr_fn(g)
+            if stream is None:
+                stream = torch.cuda.current_stream(self.device).cuda_stream
+            self.plan.step_packed(0, self.param_slab.data_ptr(), self.accum.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                  StepArgs(g, self.N, 0, lr, self.beta1_power, self.beta2_power, 0.0), 1, stream)
+            self.launches += 1
+            if self.hp.variant == ADAM:
+                self.beta1_power = _f32(np.float32(self.beta1_power) * np.float32(self.hp.beta1))
+                self.beta2_power = _f32(np.float32(self.beta2_power) * np.float32(self.hp.beta2))
+        self.global_step = g + 1
+        return applied
+
+    def stats(self) -> Dict[str, float]:
+        stream = torch.cuda.current_stream(self.device)
+        self.plan.read_stats(self._stats_host.data_ptr(), stream.cuda_stream)
+        stream.synchronize()
+        a, lr, gn, s = self._stats_host.tolist()
+        return {"applied": bool(a), "lr": lr, "global_norm": gn, "clip_scale": s}
 
 
 class HostTrainOp:

@@ -63,9 +63,13 @@ class TensorShape(tuple):
     def as_list(self):
         return list(self)
 
+    def num_elements(self):
+        return int(np.prod(self, dtype=np.int64)) if len(self) else 1
+
 
 # ------------------------------------------------------------------------------------------- graph
 _control_stack = []          # stack of lists of ops (tf.control_dependencies)
+REVERSE_UNORDERED = False    # tests flip this to evaluate unordered op sets (tf.group inputs) in reverse: exposes missing control dependencies
 
 
 class _Run:
@@ -215,10 +219,29 @@ def zeros_initializer():
     return lambda shape, dtype: np.zeros(shape, dtype=dtype.np)
 
 
+AUTO_REUSE = "AUTO_REUSE"
+_scope_stack = []
+
+
+@contextlib.contextmanager
+def variable_scope(name, reuse=None, **kw):
+    _scope_stack.append((name, reuse))
+    try:
+        yield
+    finally:
+        _scope_stack.pop()
+
+
 def get_variable(name, shape=None, dtype=float32, trainable=True, initializer=None, **kw):
+    if _scope_stack:
+        name = "/".join(n for n, _ in _scope_stack) + "/" + name
     if name in _g.by_name:
+        if any(r is AUTO_REUSE or r is True for _, r in _scope_stack):
+            return _g.by_name[name]
         raise ValueError(f"Variable {name} already exists (no reuse scope)")
-    if callable(initializer):
+    if isinstance(initializer, Tensor):
+        init = np.asarray(initializer.eval(_Run({})), dtype=dtype.np)
+    elif callable(initializer):
         init = initializer(tuple(shape), dtype)
     else:
         init = np.asarray(initializer, dtype=dtype.np).reshape(tuple(shape))
@@ -234,7 +257,7 @@ def global_variables():
 
 
 # --------------------------------------------------------------------------------------------- ops
-def constant(value, shape=None, dtype=None, name=None):
+def constant(value, dtype=None, shape=None, name=None):
     t = convert_to_tensor(value, dtype)
     if shape is not None and tuple(shape) != tuple(t.shape):
         arr = np.broadcast_to(t.eval(_Run({})), tuple(shape)).copy()
@@ -284,6 +307,8 @@ def group(*inputs, **kw):
     for i in inputs:
         flat.extend(i) if isinstance(i, (list, tuple)) else flat.append(i)
     flat = [f for f in flat if f is not None]
+    if REVERSE_UNORDERED:          # tf.group imposes no order on its inputs: an adversarial executor may run them backwards
+        flat = flat[::-1]
 
     def fn(r, *vals):
         return None
@@ -481,10 +506,72 @@ train = types.SimpleNamespace(
     get_or_create_global_step=_get_or_create_global_step,
     get_global_step=lambda: _g.global_step,
 )
-compat = types.SimpleNamespace(v1=types.SimpleNamespace(train=train))
+import sys as _sys_mod
+compat = types.SimpleNamespace(v1=_sys_mod.modules[__name__])       # `tf.compat.v1.<anything>` is this module
 math = types.SimpleNamespace(
     equal=lambda x, y, name=None: _binary(np.equal, x, y, "Equal", out_dtype=bool_),
 )
+
+
+def equal(x, y, name=None):
+    return _binary(np.equal, x, y, "Equal", out_dtype=bool_)
+
+
+# ---------------------------------------------------------------------------------- tf.load_op_library
+class _GaccumOps:
+    """What ``tf.load_op_library("libgaccum_tf.so")`` returns, emulated: the ``GaccumStep`` node of
+    tf_shim/gaccum_tf_op.cc with the semantics of the C ABI's ``gaccum_step`` (include/gaccum.h), evaluated with the
+    CPU oracle's per-op functions on the packed slabs.  TEST INFRASTRUCTURE: it lets tests execute the Python half
+    of the TensorFlow shim (graph wiring, variable creation, ordering of the scalar updates) without TensorFlow."""
+
+    @staticmethod
+    def gaccum_step(params, grads, accum, m, v, global_step, lr, beta_powers, accum_n, variant, beta1, beta2, epsilon,
+                    weight_decay_rate, clip_norm, decay_mask, name=None, **unused):
+        import os as _os
+        import sys as _sys
+        _oracle = _os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+        if _oracle not in _sys.path:
+            _sys.path.insert(0, _oracle)
+        import oracle_np as onp
+        n = len(params)
+        b1, b2, eps, wd, clip = (float(x) for x in (beta1, beta2, epsilon, weight_decay_rate, clip_norm))   # str or float attrs
+        sizes = [int(np.prod(p.value.shape)) for p in params]
+        offs, o = [], 0
+        for sz in sizes:
+            offs.append(o)
+            o += (sz + 31) // 32 * 32
+        f32 = np.float32
+
+        def fn(r, *vals):
+            gs, step, lr_v, bp = vals[:n], int(vals[n]), f32(vals[n + 1]), np.asarray(vals[n + 2], dtype=f32)
+            A, M, V = accum.value.copy(), m.value.copy(), v.value.copy()
+            view = lambda S, i: S[offs[i]:offs[i] + sizes[i]].reshape(params[i].value.shape)
+            for i in range(n):
+                if gs[i] is not None:
+                    view(A, i)[...] = np.add(view(A, i), np.asarray(gs[i], dtype=f32), dtype=f32)      # optimization.py:81,93
+            if int(np.int32(np.int64(step))) % int(accum_n) == 0:                                      # :77,91 pre-increment
+                normalized = [np.divide(np.multiply(f32(1.0), view(A, i), dtype=f32), f32(accum_n), dtype=f32) for i in range(n)]
+                if clip > 0:
+                    s_ = onp.clip_scale(onp.global_norm(normalized), clip)
+                    normalized = [np.multiply(x, s_, dtype=f32) for x in normalized]
+                for i in range(n):
+                    if int(variant) == 0:
+                        p2, m2, v2 = onp.adam_weight_decay_update(params[i].value, view(M, i), view(V, i), normalized[i], lr_v,
+                                                                  b1, b2, eps, wd, bool(decay_mask[i]))
+                    else:
+                        p2, m2, v2 = onp.adam_update(params[i].value, view(M, i), view(V, i), normalized[i], lr_v, b1, b2, eps,
+                                                     f32(bp[0]), f32(bp[1]))
+                    params[i].value = np.asarray(p2, dtype=f32)
+                    view(M, i)[...] = m2; view(V, i)[...] = v2
+                    view(A, i)[...] = f32(0.0)
+            accum.value, m.value, v.value = A, M, V
+            return None
+        ins = [convert_to_tensor(g) for g in grads] + [convert_to_tensor(global_step), convert_to_tensor(lr), convert_to_tensor(beta_powers)]
+        return Tensor(fn, ins, None, (), name or "GaccumStep")
+
+
+def load_op_library(path):
+    return _GaccumOps()
 
 
 def _no_tpu(*a, **k):

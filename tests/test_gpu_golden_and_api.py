@@ -75,6 +75,75 @@ def test_direct_apply_gradients_skips_none_pairs_like_the_reference():
             assert np.array_equal(tvars[i].tensor.cpu().numpy(), gd.z[f"param/{s}/{n}"]), f"step {s} {n}"
 
 
+def test_host_session_coalesces_arena_copies_and_matches_scattered_buffers():
+    """gaccum_step_host with gradients / parameters in a pinned arena laid out like the device slabs (one copy per
+    direction) gives exactly what separately allocated host tensors give (one copy per tensor)."""
+    import gaccum_b200 as g
+    from gaccum_b200.train_op import HostTrainOp
+    man = [("l0/kernel", (257, 33)), ("l0/bias", (33,)), ("LayerNorm/gamma", (33,)), ("emb", (70001,)), ("tail", (5,))]
+    names, shapes = [n for n, _ in man], [s for _, s in man]
+    rng = np.random.default_rng(11)
+    p0 = [rng.normal(0, 0.02, s).astype(np.float32) for s in shapes]
+    gl = [[rng.normal(0, 0.3, s).astype(np.float32) for s in shapes] for _ in range(5)]
+    hp = g.HParams.bert()
+    results = []
+    for arena in (False, True):
+        if arena:
+            _, params = HostTrainOp.pinned_arena(shapes, hp)
+            for t, x in zip(params, p0):
+                t.copy_(torch.from_numpy(x))
+        else:
+            params = [torch.from_numpy(x.copy()).pin_memory() for x in p0]
+        op = HostTrainOp(params, names, hp, 2, lambda s: 1e-2)
+        for gs in gl:
+            if arena:
+                _, gv = HostTrainOp.pinned_arena(shapes, hp)
+                for t, x in zip(gv, gs):
+                    t.copy_(torch.from_numpy(x))
+            else:
+                gv = [torch.from_numpy(x.copy()).pin_memory() for x in gs]
+            op.run(gv)
+            op.sync()
+        results.append([p.numpy().copy() for p in params])
+    assert all(np.array_equal(a, b) for a, b in zip(*results))
+    assert not all(np.array_equal(a, b) for a, b in zip(results[0], p0))
+
+
+def test_packed_inplace_handoff_matches_the_scattered_path_bit_for_bit():
+    """p.grad views of the packed accumulator (autograd accumulates in place, no accumulate launch,
+    apply without a gradient stream) give exactly what the scattered pointer-table path gives on the same micro-batches,
+    and both follow the oracle."""
+    import gaccum_b200 as g
+    from gaccum_b200.train_op import GaccumTrainOp, PackedTrainOp
+    torch.manual_seed(1)
+    names = ["dense/kernel", "dense/bias", "LayerNorm/gamma", "LayerNorm/beta", "output_weights", "output_bias"]
+
+    def make():
+        torch.manual_seed(1)
+        return torch.nn.Sequential(torch.nn.Linear(24, 40), torch.nn.LayerNorm(40), torch.nn.Tanh(), torch.nn.Linear(40, 3)).cuda()
+    xs = [torch.randn(16, 24, device="cuda") for _ in range(9)]
+    ys = [torch.randint(0, 3, (16,), device="cuda") for _ in range(9)]
+    N, lr_fn = 4, (lambda s: 5e-3)
+    ma, mb = make(), make()
+    pa, pb = list(ma.parameters()), list(mb.parameters())
+    ref = onp.ReferenceTrainOp([p.detach().cpu().numpy() for p in pa], names, onp.HParams.bert(), N, constant_lr=5e-3)
+    scattered = GaccumTrainOp(pa, names, g.HParams.bert(), N, lr_fn)
+    packed = PackedTrainOp(pb, names, g.HParams.bert(), N, lr_fn)
+    for i in range(9):
+        la = torch.nn.functional.cross_entropy(ma(xs[i]), ys[i]) * 30.0
+        ga = torch.autograd.grad(la, pa)
+        ref.run([x.cpu().numpy() for x in ga])
+        scattered.run([x.contiguous() for x in ga])
+        lb = torch.nn.functional.cross_entropy(mb(xs[i]), ys[i]) * 30.0
+        lb.backward()                                       # accumulates into the packed slab
+        assert packed.step() == (i % N == 0)
+        for k in range(len(names)):
+            assert torch.equal(pa[k], pb[k]), f"step {i} {names[k]}"
+            assert torch.equal(scattered.accum_view(k), packed.accum_view(k)) and torch.equal(scattered.m_view(k), packed.m_view(k))
+            assert np.allclose(pb[k].detach().cpu().numpy(), ref.params[k], rtol=1e-5, atol=1e-8)
+    assert packed.launches == 3 and packed.stats()["clip_scale"] < 1.0      # 9 micro-steps, 3 applies, nothing else launched
+
+
 def _tiny_model():
     torch.manual_seed(0)
     m = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.LayerNorm(32), torch.nn.Tanh(), torch.nn.Linear(32, 2)).cuda()

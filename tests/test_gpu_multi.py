@@ -113,3 +113,111 @@ def test_fused_dp_kernel_two_gpus(tmp_path):
     for i in range(T):
         assert np.allclose(r0[f"arr_{i}"], ref.params[i], rtol=1e-5, atol=1e-7)
     assert all(not r["accum"].any() for r in rs)                         # STEPS-1 is an apply step: all zero
+
+
+def _worker_host_dp(rank, world, port, outdir):
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        sys.path.insert(0, p)
+    import torch.distributed as dist
+    import gaccum_b200 as g
+    from gaccum_b200.train_op import HostTrainOp
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    rng = np.random.default_rng(5)
+    hp = g.HParams.bert()
+    _, host_params = HostTrainOp.pinned_arena([s for _, s in MAN], hp)
+    for t, (_, s) in zip(host_params, MAN):
+        t.copy_(torch.from_numpy(rng.normal(0, 0.02, s).astype(np.float32)))
+    op = HostTrainOp(host_params, [n for n, _ in MAN], hp, N, lambda s: 1e-2, device=rank)
+    op.connect_data_parallel()
+    for s in range(STEPS):
+        _, gv = HostTrainOp.pinned_arena([sh for _, sh in MAN], hp)
+        for t, x in zip(gv, _grads(rank, s, world)):
+            t.copy_(torch.from_numpy(x))
+        op.run(gv)
+        op.sync()
+    st = op.stats()
+    np.savez(os.path.join(outdir, f"hrank{rank}.npz"), *[p.numpy().copy() for p in host_params],
+             stats=np.array([st["global_norm"], st["clip_scale"]], dtype=np.float64))
+    dist.barrier()
+    del op
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_host_buffer_data_parallel_over_cuda_ipc(tmp_path):
+    """gaccum_step_host + gaccum_host_session_dp_connect: host-resident tensors, the apply step is the fused
+    NVLink exchange + apply kernel over CUDA-IPC mappings (reference 04:46,55,58,62 with CPU tensors)."""
+    import torch.multiprocessing as mp
+    import oracle_np as onp
+    ndev = torch.cuda.device_count()
+    world = 4 if ndev >= 4 else 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    mp.spawn(_worker_host_dp, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    rs = [np.load(tmp_path / f"hrank{r}.npz") for r in range(world)]
+    T = len(MAN)
+    for r in rs[1:]:
+        for i in range(T):
+            assert np.array_equal(rs[0][f"arr_{i}"], r[f"arr_{i}"]), f"replicas differ in tensor {i}"
+        assert np.array_equal(rs[0]["stats"], r["stats"])
+    rng = np.random.default_rng(5)
+    params = [rng.normal(0, 0.02, s).astype(np.float32) for _, s in MAN]
+    ref = onp.ReferenceTrainOp(params, [n for n, _ in MAN], onp.HParams.bert(), N, constant_lr=1e-2)
+    for s in range(STEPS):
+        gs = [_grads(r, s, world) for r in range(world)]
+        ref.run([np.sum([g[i] for g in gs], axis=0, dtype=np.float32) for i in range(T)])
+    for i in range(T):
+        assert np.allclose(rs[0][f"arr_{i}"], ref.params[i], rtol=1e-5, atol=1e-7)
+
+
+def _worker_fused_resume(rank, world, port, outdir):
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        sys.path.insert(0, p)
+    import torch.distributed as dist
+    import gaccum_b200 as g
+    from gaccum_b200.distributed import FusedDataParallelTrainOp
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    rng = np.random.default_rng(5)
+    names = [n for n, _ in MAN]
+    params = [torch.from_numpy(rng.normal(0, 0.02, s).astype(np.float32)).cuda() for _, s in MAN]
+    dp = FusedDataParallelTrainOp(params, names, g.HParams.bert(), N, lambda s: 1e-2)
+    for s in range(4):                                            # stop MID-WINDOW: step 3 only accumulated
+        dp.run([torch.from_numpy(x).cuda() for x in _grads(rank, s, world)])
+    sd = dp.state_dict()
+    assert any(k.endswith("/adam_m") for k in sd) and float(sd["emb/accum_grad"].abs().sum()) > 0
+    del dp
+    fresh = [torch.full(s, 7.0, device="cuda") for _, s in MAN]   # a new process would start from garbage
+    dp2 = FusedDataParallelTrainOp(fresh, names, g.HParams.bert(), N, lambda s: 1e-2)
+    dp2.load_state_dict(sd)
+    assert dp2.global_step == 4
+    for s in range(4, STEPS):
+        dp2.run([torch.from_numpy(x).cuda() for x in _grads(rank, s, world)])
+    torch.cuda.synchronize()
+    np.savez(os.path.join(outdir, f"rrank{rank}.npz"), *[p.cpu().numpy() for p in fresh])
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_fused_dp_checkpoint_resume_mid_window(tmp_path):
+    """A checkpoint taken mid-window under data parallelism (full moments gathered, accumulators summed over ranks,
+    reference names) restores into fresh replicas and continues exactly like the uninterrupted run."""
+    import torch.multiprocessing as mp
+    import oracle_np as onp
+    world = 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    mp.spawn(_worker_fused_resume, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = np.load(tmp_path / "rrank0.npz"), np.load(tmp_path / "rrank1.npz")
+    T = len(MAN)
+    rng = np.random.default_rng(5)
+    params = [rng.normal(0, 0.02, s).astype(np.float32) for _, s in MAN]
+    ref = onp.ReferenceTrainOp(params, [n for n, _ in MAN], onp.HParams.bert(), N, constant_lr=1e-2)
+    for s in range(STEPS):
+        ref.run([a + b for a, b in zip(_grads(0, s, world), _grads(1, s, world))])
+    for i in range(T):
+        assert np.array_equal(r0[f"arr_{i}"], r1[f"arr_{i}"])
+        assert np.allclose(r0[f"arr_{i}"], ref.params[i], rtol=1e-5, atol=1e-7)

@@ -225,3 +225,28 @@ def test_steps_are_cuda_graph_capturable():
         for x, y in zip(eager.params, graphed.params):
             assert torch.equal(x, y)
         assert torch.equal(eager.m, graphed.m) and torch.equal(eager.v, graphed.v) and torch.equal(eager.accum, graphed.accum)
+
+
+def test_clip_apply_is_bit_reproducible_although_tiles_are_scheduled_dynamically():
+    """The clip-apply kernel hands tiles to SMs through atomic tickets, so which SM reduces which tile changes from
+    launch to launch.  The global norm is accumulated EXACTLY (fixed-point integer atomics), so results must still be
+    bit-identical run after run -- the property data-parallel replicas rely on."""
+    import gaccum_b200 as g
+    from gaccum_b200.train_op import GaccumTrainOp
+    man = [("w%d/kernel" % i, (257, 129 + i)) for i in range(40)] + [("emb", (50000, 33)), ("b/bias", (7,)), ("LayerNorm/gamma", (3,))]
+    rng = np.random.default_rng(3)
+    p0 = [rng.normal(0, 0.02, s).astype(np.float32) for _, s in man]
+    grads = [[torch.from_numpy(rng.normal(0, 0.05, s).astype(np.float32)).cuda() for _, s in man] for _ in range(3)]
+    outs = []
+    for rep in range(4):
+        tp = [torch.from_numpy(p.copy()).cuda() for p in p0]
+        op = GaccumTrainOp(tp, [n for n, _ in man], g.HParams.bert(), 2, lambda s: 1e-3, global_step=1)
+        stats = []
+        for i in range(3):                      # accumulate, apply (clipped), accumulate
+            op.run(grads[i])
+            stats.append(op.stats())
+        assert stats[1]["applied"] and stats[1]["clip_scale"] < 1.0
+        outs.append(([t.cpu().numpy() for t in tp], op.m.cpu().numpy(), op.v.cpu().numpy(), stats[1]))
+    for o in outs[1:]:
+        assert o[3] == outs[0][3]
+        assert all(np.array_equal(a, b) for a, b in zip(o[0], outs[0][0])) and np.array_equal(o[1], outs[0][1]) and np.array_equal(o[2], outs[0][2])
