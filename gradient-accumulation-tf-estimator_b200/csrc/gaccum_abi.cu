@@ -63,7 +63,7 @@ struct gaccum_plan {
   uint32_t* d_dp_sync = nullptr;           // data-parallel kernel: block-completion counters (zero between launches)
   unsigned long long* d_barrier = nullptr; // clip-apply kernel: monotonic arrival counter of the consumers' grid barrier
   LaunchCounters* d_counters = nullptr;    // ... two sets of per-launch counters (tickets, pool length, norm accumulator)
-  uint32_t* d_pool_list = nullptr;         // ... one flag per tile: a' parked in Tensor Memory between the passes
+  bool p1_dynamic = false;                 // ... pass 1 hands out the non-parked tiles by atomic tickets (long passes) or by position (short ones)
   int tmem_tiles = kTmemTiles;             // tiles of a' per consumer group parked in Tensor Memory (GACCUM_TMEM_TILES: A/B)
 #ifdef GACCUM_EXPERIMENTS
   unsigned long long* d_debug = nullptr;   // per-CTA timestamps (tools/cta_timeline.py; experiments build only)
@@ -191,7 +191,7 @@ static int launch_apply_clip(gaccum_plan* pl, KernelParams<CAP>& prm, cudaStream
   const int grid = std::max(1, std::min(pl->num_sms, ((int)pl->tiles.size() + kGroups - 1) / kGroups));
   prm.barrier = pl->d_barrier;
   prm.counters = pl->d_counters;
-  prm.parked = pl->d_pool_list;
+  if (pl->p1_dynamic) prm.flags |= kFlagDynamicPass1;
   prm.tmem_tiles = pl->tmem_tiles;
   void* args[] = {(void*)&prm};
   CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kClipThreads), args, (size_t)kRingBytes, st));
@@ -298,7 +298,7 @@ static int check_args(const gaccum_step_args* a) {
 }
 
 static void free_plan_device(gaccum_plan* pl) {
-  cudaFree(pl->d_tiles); cudaFree(pl->d_partials); cudaFree(pl->d_stats); cudaFree(pl->d_dp_sync); cudaFree(pl->d_barrier); cudaFree(pl->d_counters); cudaFree(pl->d_pool_list);
+  cudaFree(pl->d_tiles); cudaFree(pl->d_partials); cudaFree(pl->d_stats); cudaFree(pl->d_dp_sync); cudaFree(pl->d_barrier); cudaFree(pl->d_counters);
 #ifdef GACCUM_EXPERIMENTS
   cudaFree(pl->d_debug);
 #endif
@@ -398,6 +398,10 @@ int gaccum_plan_create(gaccum_plan** out, int32_t T, const int64_t* numels, cons
   // GACCUM_TMEM_TILES: A/B measurement knob of the clip-apply kernel (how many a' tiles per group are parked in
   // Tensor Memory); every value computes the same result.  Result-changing timing experiments do not exist in this build.
   if (const char* t = getenv("GACCUM_TMEM_TILES")) pl->tmem_tiles = std::max(0, std::min(kTmemTiles, atoi(t)));
+  // measured on the same GPU (profiles/r02_tune_sweep.md): handing pass 1's non-parked tiles out by tickets is as fast as
+  // the static split at BERT-Small (176.5 vs 177.0 us) and 1.5-2 % faster at BERT-Base / -Large; GACCUM_P1_DYNAMIC=0 is the A/B knob
+  pl->p1_dynamic = true;
+  if (const char* t = getenv("GACCUM_P1_DYNAMIC")) pl->p1_dynamic = atoi(t) != 0;
   if (device >= 0) {
     int n = gaccum_device_count();
     if (device >= n) { delete pl; return fail(GACCUM_ENODEVICE, "CUDA device %d requested but %d device(s) visible; libgaccum has no CPU fallback", device, n); }
@@ -420,7 +424,6 @@ int gaccum_plan_create(gaccum_plan** out, int32_t T, const int64_t* numels, cons
     if (e == cudaSuccess) e = cudaMemset(pl->d_barrier, 0, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_counters, 2 * sizeof(LaunchCounters));
     if (e == cudaSuccess) e = cudaMemset(pl->d_counters, 0, 2 * sizeof(LaunchCounters));
-    if (e == cudaSuccess) e = cudaMalloc(&pl->d_pool_list, sizeof(uint32_t) * std::max<size_t>(1, pl->tiles.size()));
 #ifdef GACCUM_EXPERIMENTS
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_debug, sizeof(unsigned long long) * 16 * (size_t)pl->max_grid);
     if (e == cudaSuccess) e = cudaMemset(pl->d_debug, 0, sizeof(unsigned long long) * 16 * (size_t)pl->max_grid);

@@ -90,7 +90,6 @@ struct KernelParams {
   uint32_t flags;     // kFlag* bits (all of them produce correct results)
   unsigned long long* barrier;  // apply_clip_kernel: monotonic arrival counter of the consumers' grid barrier
   struct LaunchCounters* counters;  // apply_clip_kernel: two sets of per-launch counters (tickets, pool length, norm accumulator)
-  uint32_t* parked;             // apply_clip_kernel: num_tiles flags written in pass 1: 1 = a' of the tile is parked in some SM's Tensor Memory
   int32_t tmem_tiles;   // apply_clip_kernel: tiles of a' each consumer group parks in Tensor Memory (0..kTmemTiles)
 #ifdef GACCUM_EXPERIMENTS
   unsigned long long* debug;  // 16 words per CTA: 4 timestamps (ns) + wait-cycle counters (tools/cta_timeline.py)
@@ -99,7 +98,8 @@ struct KernelParams {
   PtrTable<CAP> tab;
 };
 
-constexpr uint32_t kFlagAssign = 1u;        // accumulate_kernel stores G instead of adding it (host-session gather of small tensors)
+constexpr uint32_t kFlagAssign = 1u;        // accumulate_kernel stores G instead of adding it
+constexpr uint32_t kFlagDynamicPass1 = 2u;  // apply_clip_kernel: pass 1 hands the non-parked tiles out by atomic tickets instead of by position
 
 // ---------------------------------------------------------------------------------------------
 // memory helpers: G is read exactly once -> streaming (evict-first) loads; zeroing the
@@ -396,14 +396,14 @@ constexpr int kTmemColsPerWarp = 80;              // 6 warps share a lane quadra
 constexpr int kTmemTiles = kTmemColsPerWarp / 8;  // 10 tiles per group
 constexpr uint32_t kNoTmem = 0xffffffffu;
 #ifndef GACCUM_P1_SLOTS
-#define GACCUM_P1_SLOTS 4
+#define GACCUM_P1_SLOTS 2
 #endif
 constexpr int kP1Slots = GACCUM_P1_SLOTS;         // pass-1 ring slots per group, 16 KB each
 constexpr int kP1SlotVecs = 2 * (kTile / 4);      // float4 per pass-1 slot: G | a
 constexpr int kP2SlotVecs = 4 * (kTile / 4);      // float4 per pass-2 slot: p | m | v | a'
 constexpr int kRingVecs = kP1Slots * kP1SlotVecs; // per group
-constexpr int kP2Slots = kRingVecs / kP2SlotVecs; // 4 x 16 KB = 64 KB -> 2 x 32 KB
-constexpr int kRingBytes = kGroups * kRingVecs * 16;   // dynamic shared memory of the kernel (192 KB)
+constexpr int kP2Slots = kRingVecs / kP2SlotVecs; // 2 x 16 KB = 32 KB -> 1 x 32 KB (deeper rings measured slower: r02_tune_sweep.md)
+constexpr int kRingBytes = kGroups * kRingVecs * 16;   // dynamic shared memory of the kernel (96 KB)
 static_assert(kP2Slots >= 1 && kP1Slots <= 8, "ring must hold at least one [p|m|v|a'] slot");
 constexpr int kMaxSlots = 8;
 constexpr int kTicketBatch = 4;                   // pass-1 tickets a producer draws at once while plenty of tiles are left
@@ -694,15 +694,17 @@ apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
   __shared__ uint32_t s_tmem_base, s_set;
   __shared__ __align__(8) uint64_t s_full1[kGroups][kMaxSlots], s_empty1[kGroups][kMaxSlots];
   __shared__ __align__(8) uint64_t s_full2[kGroups][kMaxSlots], s_empty2[kGroups][kMaxSlots];
-  __shared__ __align__(8) uint64_t s_go[kGroups], s_p1done[kGroups];
+  __shared__ __align__(8) uint64_t s_go[kGroups];
   __shared__ SlotMeta s_meta1[kGroups][kMaxSlots], s_meta2[kGroups][kMaxSlots];
-  __shared__ SlotMeta s_own[kGroups][kTmemTiles];          // tiles whose a' this group parked in Tensor Memory
-  __shared__ int s_nown[kGroups];
 
   const int warp = (int)threadIdx.x >> 5;
   const bool is_producer = warp >= kConsumerThreads / 32;
   const int grp = is_producer ? warp - kConsumerThreads / 32 : (int)threadIdx.x / kThreads;   // group served / group id
   const int nt = prm.num_tiles, G = (int)gridDim.x * kGroups;
+  const int b = (int)blockIdx.x * kGroups + grp;                   // virtual block id
+  const int C = b < nt ? (nt - 1 - b) / G + 1 : 0;                 // tiles b, b + G, ... of this group's static share
+  const int n_tm = min(prm.tmem_tiles, C);                         // own tiles: a' parked in Tensor Memory
+  const int pool_lo = min(nt, prm.tmem_tiles * G);                 // tiles [pool_lo, nt): a' goes back to global memory
   float4* const ring = reinterpret_cast<float4*>(smem_dyn) + (size_t)grp * kRingVecs;
   const uint64_t pol_last = policy_evict_last();
 
@@ -729,8 +731,7 @@ apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
     for (int g = 0; g < kGroups; ++g) {
       for (int sl = 0; sl < kP1Slots; ++sl) { mbar_init(&s_full1[g][sl], 1); mbar_init(&s_empty1[g][sl], kThreads / 32); }
       for (int sl = 0; sl < kP2Slots; ++sl) { mbar_init(&s_full2[g][sl], 1); mbar_init(&s_empty2[g][sl], kThreads / 32); }
-      mbar_init(&s_go[g], 1); mbar_init(&s_p1done[g], 1);
-      s_nown[g] = 0;
+      mbar_init(&s_go[g], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -755,54 +756,74 @@ apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
     long long dbg_empty = 0;
     const long long dbg_p0 = clock64();
 #endif
-    // ---- pass 1: tickets over all tiles, kTicketBatch at a time while plenty are left (one atomic per lane, the
-    //      descriptor loads of a batch overlap), single tickets near the end so that no SM is left holding a batch ----
+    // ---- pass 1.  First the group's OWN tiles b + j*G, j < tmem_tiles: their a' is parked in this SM's Tensor Memory, so
+    //      they are bound to it in both passes.  Then the rest of the model, tiles [pool_lo, nt): either this group's static
+    //      share (b + j*G) or, with kFlagDynamicPass1, whatever the global ticket counter hands out -- kTicketBatch tickets at
+    //      a time while plenty are left (one atomic per lane, the descriptor loads of a batch overlap), single tickets
+    //      near the end so that no SM is left holding a batch ----
     {
       RingPos rp;
-      bool done = false;
-      unsigned long long last = 0;
+      auto issue = [&](const TileDesc& dl, const uint32_t tile) {          // lane 0 only
+        const float* g = nullptr;
+        if constexpr (HAS_G) g = grad_ptr(prm.tab, dl);
+        const uint32_t nvec = bulk_vecs(dl, g);
+        uint64_t* full = &s_full1[grp][rp.slot];
+#ifdef GACCUM_EXPERIMENTS
+        const long long t_e0 = clock64();
+#endif
+        mbar_wait(&s_empty1[grp][rp.slot], (rp.use & 1u) ^ 1u);             // the consumers have released the slot
+#ifdef GACCUM_EXPERIMENTS
+        dbg_empty += clock64() - t_e0;
+#endif
+        SlotMeta* meta = &s_meta1[grp][rp.slot];
+        meta->d = dl;
+        meta->tile = tile;
+        if (nvec > 0) {
+          float4* dst = ring + (size_t)rp.slot * kP1SlotVecs;
+          mbar_arrive_expect_tx(full, nvec * 16u * (g ? 2u : 1u));
+          if (g) bulk_g2s(dst, g, nvec * 16u, full, pol_first);
+          bulk_g2s(dst + kTile / 4, prm.accum + (size_t)dl.soff32 * kSlabAlign, nvec * 16u, full, pol_first);
+        } else {
+          mbar_arrive(full);                                                 // nothing to copy: complete the phase
+        }
+      };
+      auto shuffled = [&](const TileDesc& d, int l) {
+        TileDesc dl;
+        dl.tensor_flags = __shfl_sync(0xffffffffu, d.tensor_flags, l);
+        dl.len = __shfl_sync(0xffffffffu, d.len, l);
+        dl.toff = __shfl_sync(0xffffffffu, d.toff, l);
+        dl.soff32 = __shfl_sync(0xffffffffu, d.soff32, l);
+        return dl;
+      };
+      const bool dynamic = (prm.flags & kFlagDynamicPass1) != 0;
+      const int n_static = dynamic ? n_tm : C;                                // tiles b + j*G, j < n_static, are this group's by position
+      for (int j0 = 0; j0 < n_static; j0 += 32) {                              // descriptors 32 at a time, one per lane
+        TileDesc d{};
+        if (j0 + lane < n_static) d = prm.tiles[b + (j0 + lane) * G];
+        const int nb = min(32, n_static - j0);
+        for (int l = 0; l < nb; ++l) {
+          const TileDesc dl = shuffled(d, l);
+          if (lane == 0) issue(dl, (uint32_t)(b + (j0 + l) * G));
+          rp.advance(kP1Slots);
+        }
+      }
+      bool done = !dynamic;
+      long long last = pool_lo;
       while (!done) {
-        const long long left = (long long)nt - (long long)last;
+        const long long left = (long long)nt - last;
         const int batch = left > 8ll * G ? kTicketBatch : (left > 2ll * G ? 2 : 1);
-        unsigned long long tk = ~0ull;
+        long long tile = nt;
         TileDesc d{};
         if (lane < batch) {
-          tk = atomicAdd(&ctr->p1_ticket, 1ull);
-          if (tk < (unsigned long long)nt) d = prm.tiles[tk];
+          tile = (long long)pool_lo + (long long)atomicAdd(&ctr->p1_ticket, 1ull);
+          if (tile < nt) d = prm.tiles[tile];
         }
         for (int l = 0; l < batch; ++l) {
-          const unsigned long long tkl = __shfl_sync(0xffffffffu, tk, l);
-          if (tkl >= (unsigned long long)nt) { done = true; continue; }      // lanes get their tickets in no particular order:
-          last = tkl;                                                        // a valid one may follow an exhausted one
-          TileDesc dl;
-          dl.tensor_flags = __shfl_sync(0xffffffffu, d.tensor_flags, l);
-          dl.len = __shfl_sync(0xffffffffu, d.len, l);
-          dl.toff = __shfl_sync(0xffffffffu, d.toff, l);
-          dl.soff32 = __shfl_sync(0xffffffffu, d.soff32, l);
-          if (lane == 0) {
-            const float* g = nullptr;
-            if constexpr (HAS_G) g = grad_ptr(prm.tab, dl);
-            const uint32_t nvec = bulk_vecs(dl, g);
-            uint64_t* full = &s_full1[grp][rp.slot];
-#ifdef GACCUM_EXPERIMENTS
-            const long long t_e0 = clock64();
-#endif
-            mbar_wait(&s_empty1[grp][rp.slot], (rp.use & 1u) ^ 1u);         // the consumers have released the slot
-#ifdef GACCUM_EXPERIMENTS
-            dbg_empty += clock64() - t_e0;
-#endif
-            SlotMeta* meta = &s_meta1[grp][rp.slot];
-            meta->d = dl;
-            meta->tile = (uint32_t)tkl;
-            if (nvec > 0) {
-              float4* dst = ring + (size_t)rp.slot * kP1SlotVecs;
-              mbar_arrive_expect_tx(full, nvec * 16u * (g ? 2u : 1u));
-              if (g) bulk_g2s(dst, g, nvec * 16u, full, pol_first);
-              bulk_g2s(dst + kTile / 4, prm.accum + (size_t)dl.soff32 * kSlabAlign, nvec * 16u, full, pol_first);
-            } else {
-              mbar_arrive(full);                                             // nothing to copy: complete the phase
-            }
-          }
+          const long long tl = __shfl_sync(0xffffffffu, tile, l);
+          if (tl >= nt) { done = true; continue; }       // lanes get their tickets in no particular order: a valid one may follow
+          last = tl;
+          const TileDesc dl = shuffled(d, l);
+          if (lane == 0) issue(dl, (uint32_t)tl);
           rp.advance(kP1Slots);
         }
       }
@@ -831,15 +852,14 @@ apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
     //      in the slot's 4th quarter; they may only be fetched once every CTA has passed the barrier. ----
     if (lane == 0) {
       RingPos rp;
-      mbar_wait(&s_p1done[grp], 0);             // the group's leader has recorded its last parked tile
-      const int n_own = s_nown[grp];
       int jb = 0;
       bool past_barrier = false;
+      const unsigned long long pool_n = (unsigned long long)max(0, nt - pool_lo);
       while (true) {
-        TileDesc d;
+        int tile;
         uint32_t tmem_slot = kNoTmem;
-        if (jb < n_own) {
-          d = s_own[grp][jb].d;
+        if (jb < n_tm) {
+          tile = b + jb * G;
           tmem_slot = (uint32_t)jb;
           ++jb;
         } else {
@@ -849,20 +869,23 @@ apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
             past_barrier = true;
           }
           const unsigned long long tk = atomicAdd(&ctr->p2_ticket, 1ull);
-          if (tk >= (unsigned long long)nt) break;
-          const int tile = nt - 1 - (int)tk;                                    // youngest a' lines first
-          const uint32_t is_parked = __ldcg(prm.parked + tile);                 // (both loads depend on the ticket only: they overlap)
-          d = prm.tiles[tile];
-          if (is_parked) continue;                                              // its owner updates it from Tensor Memory
+          if (tk >= pool_n) break;
+          tile = nt - 1 - (int)tk;                                              // youngest a' lines first
         }
+        const TileDesc d = prm.tiles[tile];
         const float* p = param_ptr(prm.tab, d);
         const uint32_t nvec = bulk_vecs2(d, p);
-        const bool in_tmem = tmem_slot != kNoTmem;
+        const bool in_tmem = tmem_slot != kNoTmem && tmem_ok<HAS_G>(d, prm);
+        if (!in_tmem && !past_barrier) {                                        // an own tile whose a' had to go to global memory
+          mbar_wait(&s_go[grp], 0);
+          asm volatile("fence.proxy.async;" ::: "memory");
+          past_barrier = true;
+        }
         uint64_t* full = &s_full2[grp][rp.slot];
         mbar_wait(&s_empty2[grp][rp.slot], (rp.use & 1u) ^ 1u);
         SlotMeta* meta = &s_meta2[grp][rp.slot];
         meta->d = d;
-        meta->tmem_slot = tmem_slot;
+        meta->tmem_slot = in_tmem ? tmem_slot : kNoTmem;
         if (nvec > 0) {
           const size_t soff = (size_t)d.soff32 * kSlabAlign;
           float4* dst = ring + (size_t)rp.slot * kP2SlotVecs;
@@ -892,7 +915,7 @@ apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
     unsigned int my_nonfinite = 0;
     {
       RingPos rp;
-      int n_parked = 0;
+      int n_seen = 0;
       while (true) {
 #ifdef GACCUM_EXPERIMENTS
         const long long t_w0 = clock64();
@@ -903,23 +926,18 @@ apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
 #endif
         const SlotMeta meta = s_meta1[grp][rp.slot];
         if (meta.d.len == 0) break;
-        // Tensor Memory takes the first kTmemTiles FULL, vector-path tiles this group sees (tcgen05.st/ld are warp-collective)
-        const bool park = n_parked < prm.tmem_tiles && tmem_ok<HAS_G>(meta.d, prm);
-        const uint32_t tm = park ? tmem_slot_addr(tmem_base, n_parked) : kNoTmem;
+        // Tensor Memory takes the group's own tiles j < tmem_tiles (the first ones it is handed) when they are FULL,
+        // vector-path tiles (tcgen05.st/ld are warp-collective)
+        const bool own = n_seen < n_tm;
+        const bool park = own && tmem_ok<HAS_G>(meta.d, prm);
+        const uint32_t tm = park ? tmem_slot_addr(tmem_base, n_seen) : kNoTmem;
         const float part = norm_tile<HAS_G>(meta.d, prm, ring + (size_t)rp.slot * kP1SlotVecs, &s_empty1[grp][rp.slot], tm, pol_last);
-        // warp total in fp64, fixed butterfly order; lane 0 adds it EXACTLY into the CTA's accumulator
+        // warp total in fp64, fixed butterfly order; lane 0 adds it EXACTLY into its warp's accumulator
         double w = (double)part;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
         if ((threadIdx.x & 31) == 0) acc_add(s_bins[warp], my_nonfinite, w);
-        if (leader) {
-          if (park) {
-            s_own[grp][n_parked] = meta;                      // remembered for pass 2 (this group's producer reads it after pass 1)
-            s_nown[grp] = n_parked + 1;
-          }
-          prm.parked[meta.tile] = park ? 1u : 0u;             // 0: any SM may update this tile in pass 2 (plain store, nobody waits for it)
-        }
-        n_parked += park ? 1 : 0;
+        ++n_seen;
         rp.advance(kP1Slots);
       }
     }
@@ -929,7 +947,6 @@ apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
       prm.debug[blockIdx.x * 16 + 10 + grp] = (unsigned long long)(clock64() - dbg_t0);   // cycles of the group's pass 1
     }
 #endif
-    if (leader) mbar_arrive(&s_p1done[grp]);                 // s_own / s_nown of this group are final
     named_bar_sync(1, kConsumerThreads);                     // every consumer thread of this CTA is through pass 1
     // flush this CTA's accumulators into the launch's global one (integer adds: order does not matter)
     if (my_nonfinite) atomicOr(&s_nonfinite, my_nonfinite);
