@@ -373,6 +373,16 @@ def run_b200_arm(args):
     apply_ms = [p for p, k in zip(per, kinds) if k]
     acc_ms = [p for p, k in zip(per, kinds) if not k]
     mean = lambda x: (sum(x) / len(x)) if x else float("nan")
+    per_rank = None
+    if dist is not None:
+        # every rank's own per-kind means and total: a straggler (slower GPU, later launches) shows up here, not in rank 0's numbers
+        mine = torch.tensor([mean(apply_ms) if apply_ms else 0.0, mean(acc_ms) if acc_ms else 0.0, evs[0].elapsed_time(evs[K])],
+                            device=dev, dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"apply_step_us": [round(float(t[0]) * 1e3, 1) for t in allr],
+                    "accumulate_us": [round(float(t[1]) * 1e3, 1) for t in allr],
+                    "timed_region_ms": [round(float(t[2]), 3) for t in allr]}
 
     # ---- e2e: the C ABI's host-buffer entry point (gaccum_step_host): parameters and gradients
     #      live in pinned HOST memory; H2D of every micro-step's gradients, D2H of the stats block
@@ -455,7 +465,7 @@ def run_b200_arm(args):
     a_ms, c_ms = mean(apply_ms), mean(acc_ms)
     achieved = ab / (a_ms * 1e-3) / 1e9 if apply_ms else float("nan")
     if world == 1:
-        kernel = ("apply_clip_kernel (a+=G, /N, global-norm clip, AdamWeightDecay, a=0; one cooperative launch, TMA-fed pass 1)"
+        kernel = ("apply_clip_kernel (a+=G, /N, global-norm clip, AdamWeightDecay, a=0; one cooperative launch: TMA-fed rings, ticketed tiles, Tensor-Memory stash, exact norm)"
                   if hp.clip_norm > 0 else "apply_kernel (single pass: a+=G, /N, Adam, a=0; no clip)")
     else:
         kernel = "dp_apply_kernel (apply step at N>1: includes the NVLink exchange, so this is not an HBM roofline)"
@@ -493,6 +503,8 @@ def run_b200_arm(args):
     }
     if parity is not None:
         out["parity"] = parity
+    if per_rank is not None:
+        out["per_rank"] = per_rank
     if e2e:
         out["e2e"] = e2e
     if with_model:

@@ -60,7 +60,7 @@ struct gaccum_plan {
   TileDesc* d_tiles = nullptr;
   double* d_partials = nullptr;
   float* d_stats = nullptr;
-  uint32_t* d_dp_sync = nullptr;           // data-parallel kernel: block-completion counters (zero between launches)
+  uint32_t* d_dp_sync = nullptr;           // data-parallel kernel: block-completion counters and tile tickets (zero between launches)
   unsigned long long* d_barrier = nullptr; // clip-apply kernel: monotonic arrival counter of the consumers' grid barrier
   LaunchCounters* d_counters = nullptr;    // ... two sets of per-launch counters (tickets, pool length, norm accumulator)
   bool p1_dynamic = false;                 // ... pass 1 hands out the non-parked tiles by atomic tickets (long passes) or by position (short ones)
@@ -417,7 +417,7 @@ int gaccum_plan_create(gaccum_plan** out, int32_t T, const int64_t* numels, cons
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_tiles, tb);
     if (e == cudaSuccess && !pl->tiles.empty())
       e = cudaMemcpy(pl->d_tiles, pl->tiles.data(), pl->tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc(&pl->d_partials, sizeof(double) * (size_t)pl->max_grid);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_partials, sizeof(double) * std::max<size_t>((size_t)pl->max_grid, pl->tiles.size()));   // per CTA (clip-apply) / per tile (data-parallel apply)
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_dp_sync, sizeof(uint32_t) * 8);
     if (e == cudaSuccess) e = cudaMemset(pl->d_dp_sync, 0, sizeof(uint32_t) * 8);
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_barrier, sizeof(unsigned long long));
@@ -596,6 +596,9 @@ static int do_apply_dp(gaccum_plan* pl, const gaccum_dp_comm* comm, const float*
   prm->partials = pl->d_partials;
   prm->stats = pl->d_stats;
   prm->sync = pl->d_dp_sync;
+#ifdef GACCUM_EXPERIMENTS
+  prm->debug = pl->d_debug;
+#endif
   prm->sc = make_scalars(pl->hp, a);
   prm->rank = comm->rank;
   prm->world = W;
@@ -605,6 +608,7 @@ static int do_apply_dp(gaccum_plan* pl, const gaccum_dp_comm* comm, const float*
   int grid = 0;
   int rc = grid_for(pl, fn, &grid);
   if (rc == GACCUM_OK) {
+    if (const char* t = getenv("GACCUM_DP_BLOCKS_PER_SM")) grid = std::min(grid, std::max(1, atoi(t)) * pl->num_sms);   // A/B knob
     grid = std::max(1, std::min(grid, prm->num_tiles));
     void* args[] = {(void*)prm};
     cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, 0, st);

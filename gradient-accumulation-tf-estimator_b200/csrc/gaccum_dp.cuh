@@ -14,6 +14,7 @@
 //             (optimization.py:86-87).  Each rank starts its sweep at its right-hand neighbour's shard, so
 //             at any moment every owner receives from about one source.        == reduce-scatter, push
 //   flag 0    "all my pushes have landed" (block-completion counter -> system-scope release flags)
+//   (tiles of every phase are handed to the blocks by atomic tickets: the blocks finish together)
 //   phase B   owned tiles: a' = sum over ranks 0..W-1 of their contribution (own: a, others: staging),
 //             FIXED rank order => deterministic; a <- a'; partial sum((a'/N)^2)
 //   flag 1    per-rank partial norms travel with the flag; every rank adds the W partials in rank
@@ -62,7 +63,10 @@ struct DpParams {
   float* v;
   double* partials;
   float* stats;
-  uint32_t* sync;                       // 3 block-completion counters, zero between launches
+  uint32_t* sync;                       // [0..2] block-completion counters, [3], [5] tile tickets of phases A and C; zero between launches
+#ifdef GACCUM_EXPERIMENTS
+  unsigned long long* debug;            // 16 timestamps (ns) per block (tools/dp_timeline.py)
+#endif
   Scalars sc;
   int32_t rank, world;
   uint32_t epoch;
@@ -76,24 +80,69 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// End of a phase on this rank: every thread orders its (local and remote) stores at system scope, the block
+// End of a phase on this rank: the block's (local and remote) stores are ordered at system scope, the block
 // bumps the phase's completion counter, and the LAST block to arrive raises this rank's flag in every
-// rank's control block (its own included).  `extra` lets the last block publish the norm first.
+// rank's control block (its own included).  `extra` (run by ALL threads of that last block, before the flags go
+// up) lets it publish the norm first.
 template <int CAP, typename F>
 __device__ __forceinline__ void dp_phase_done(const DpParams<CAP>& prm, int phase, F&& extra) {
-  __threadfence_system();
+  __shared__ int s_last;
+  // bar.sync orders every thread's stores before thread 0's fence, and a system-scope fence is cumulative: ONE
+  // MEMBAR.SYS per block publishes the whole block's local and remote stores (one per thread -- 150 000 of them,
+  // all at the end of a phase -- cost 30 us per phase)
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence_system();
-    const bool last = atomicAdd(prm.sync + phase, 1u) == gridDim.x - 1;
-    if (last) {
-      __threadfence_system();            // acquire side of the counter chain
-      prm.sync[phase] = 0;               // re-arm for the next launch (nobody touches it again in this one)
-      extra();
+    s_last = atomicAdd(prm.sync + phase, 1u) == gridDim.x - 1;
+#ifdef GACCUM_EXPERIMENTS
+    if (prm.debug && phase == 1) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); prm.debug[blockIdx.x * 16 + 9] = t; }
+#endif
+  }
+  __syncthreads();
+  if (s_last) {                                // block-uniform
+    if (threadIdx.x == 0) {
+      __threadfence_system();                  // acquire side of the counter chain
+      prm.sync[phase] = 0;                     // re-arm for the next launch (nobody touches it again in this one)
+      if (phase == 2) { prm.sync[3] = 0; prm.sync[4] = 0; prm.sync[5] = 0; }   // every block has left its last ticket loop
+    }
+    extra();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
       for (int w = 0; w < prm.world; ++w) st_release_sys(prm.ctrl[w] + phase * kMaxRanks + prm.rank, prm.epoch);
+#ifdef GACCUM_EXPERIMENTS
+      if (prm.debug && phase == 1) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); prm.debug[blockIdx.x * 16 + 10] = t; }
+#endif
     }
   }
 }
+// Tiles of a phase are handed to the blocks by an atomic ticket counter (SMs see different shares of HBM and NVLink
+// bandwidth: with a static split the first block finished phase A 40 us before the last).  The block works on ticket i
+// while every thread already holds ticket i+1 (so the caller can load that tile's descriptor) and thread 0 draws
+// ticket i+2: neither the atomic's round trip nor the descriptor load is on the critical path.
+struct TicketLoop {
+  uint32_t* ctr;
+  int* slot;      // 3 ints of shared memory
+  int it;
+  int cur, nxt;
+  __device__ __forceinline__ void begin(uint32_t* counter, int* s_slot) {
+    ctr = counter; slot = s_slot; it = 0;
+    if (threadIdx.x == 0) { slot[0] = (int)atomicAdd(ctr, 1u); slot[1] = (int)atomicAdd(ctr, 1u); }
+    __syncthreads();
+    cur = slot[0]; nxt = slot[1];
+  }
+  // top of an iteration: thread 0 draws the ticket after next
+  __device__ __forceinline__ void prefetch() {
+    if (threadIdx.x == 0) slot[(it + 2) % 3] = (int)atomicAdd(ctr, 1u);
+  }
+  // bottom of an iteration
+  __device__ __forceinline__ void advance() {
+    __syncthreads();
+    ++it;
+    cur = nxt;
+    nxt = slot[(it + 1) % 3];
+  }
+};
 // Every block: wait until all W ranks have raised `phase` for this epoch (polling this rank's own control block)
 template <int CAP>
 __device__ __forceinline__ void dp_wait(const DpParams<CAP>& prm, int phase) {
@@ -288,37 +337,92 @@ dp_apply_kernel(const __grid_constant__ DpParams<CAP> prm) {
   __shared__ double red[kThreads / 32];
   __shared__ float s_bcast[2];
   const uint64_t pol = policy_evict_last();
-  const int W = prm.world, R = prm.rank, nt = prm.num_tiles, G = (int)gridDim.x;
+  const int W = prm.world, R = prm.rank, nt = prm.num_tiles;
   const int lo = prm.bounds[R], hi = prm.bounds[R + 1];
+#ifdef GACCUM_EXPERIMENTS
+  auto stamp = [&](int which) {
+    if (prm.debug && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      prm.debug[blockIdx.x * 16 + which] = t;
+    }
+  };
+#else
+  auto stamp = [](int) {};
+#endif
+  stamp(0);
 
-  // ---- phase A: local accumulate + reduce-scatter by pushes.  The sweep starts at the right-hand
-  //      neighbour's shard: owner (R+1+j) % W is being written by rank R while rank R+1 writes (R+2+j) % W ... ----
+  __shared__ int s_ticket[3];
+  TicketLoop tl;
+  // ---- phase A: local accumulate + reduce-scatter by pushes.  Ticket q -> tile i = q / W of shard (R + 1 + q % W) % W:
+  //      consecutive tickets go to W different owners (the last one is this rank itself), so pushes to every peer are
+  //      spread evenly over the whole phase instead of arriving in one burst that NVLink then needs 30 us to drain, and
+  //      at any moment every owner receives from every source at the same rate ----
   {
-    const int start = prm.bounds[(R + 1) % W];
-    for (int q = (int)blockIdx.x; q < nt; q += G) {
-      int t = q + start;
-      if (t >= nt) t -= nt;
-      dp_push_tile(prm.tiles[t], t, prm, pol);
+    int max_shard = 0;
+    for (int w = 0; w < W; ++w) max_shard = max(max_shard, prm.bounds[w + 1] - prm.bounds[w]);
+    const int nq = max_shard * W;
+    auto tile_of = [&](int q) -> int {
+      if (q >= nq) return -1;
+      int o = R + 1 + q % W;
+      if (o >= W) o -= W;
+      const int t = prm.bounds[o] + q / W;
+      return t < prm.bounds[o + 1] ? t : -1;
+    };
+    tl.begin(prm.sync + 3, s_ticket);
+    int t = tile_of(tl.cur);
+    TileDesc d{};
+    if (t >= 0) d = prm.tiles[t];
+    while (tl.cur < nq) {
+      tl.prefetch();
+      const int tn = tile_of(tl.nxt);
+      TileDesc dn{};
+      if (tn >= 0) dn = prm.tiles[tn];                      // next descriptor: in flight while this tile is processed
+      if (t >= 0) dp_push_tile(d, t, prm, pol);
+      tl.advance();
+      t = tn; d = dn;
     }
   }
+  stamp(1);
   dp_phase_done(prm, 0, [] {});
+  stamp(2);
   dp_wait(prm, 0);
+  stamp(3);
 
-  // ---- phase B: deterministic reduction of the owned shard + norm partial -------------------------
-  double acc = 0.0;
-  for (int t = lo + (int)blockIdx.x; t < hi; t += G) acc += (double)dp_reduce_tile(prm.tiles[t], prm, pol);
-  const double part = block_reduce_to_double(acc, red);
-  if (threadIdx.x == 0) prm.partials[blockIdx.x] = part;
+  // ---- phase B: reduction of the owned shard in fixed rank order + norm partial.  Local traffic only and short: a static
+  //      split (block b takes owned tiles b, b + G, ...) beats tickets here (31 vs 48 us at W=2: per-tile barriers
+  //      cost more than the imbalance), and keeps the reduction order fixed: thread fp64 running sums -> block tree ->
+  //      one partial per block -> the last block adds the partials in block order ---------------------------------
+  {
+    double acc = 0.0;
+    const int G = (int)gridDim.x;
+    int t = lo + (int)blockIdx.x;
+    TileDesc d{};
+    if (t < hi) d = prm.tiles[t];
+    while (t < hi) {
+      TileDesc dn{};
+      if (t + G < hi) dn = prm.tiles[t + G];
+      acc += (double)dp_reduce_tile(d, prm, pol);
+      t += G; d = dn;
+    }
+    const double part = block_reduce_to_double(acc, red);
+    if (threadIdx.x == 0) prm.partials[blockIdx.x] = part;
+  }
+  stamp(4);
   dp_phase_done(prm, 1, [&] {
-    // last block of this rank: per-block partials in block order -> this rank's partial norm -> every rank
+    // last block of this rank: per-block partials, fixed tree -> this rank's partial norm -> every rank
     double tot = 0.0;
-    for (int i = 0; i < G; ++i) tot += __ldcg(prm.partials + i);
-    for (int w = 0; w < W; ++w) {
-      double* slot = reinterpret_cast<double*>(reinterpret_cast<char*>(prm.ctrl[w]) + kCtrlNormByteOffset) + R;
-      asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(slot), "d"(tot) : "memory");
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += kThreads) tot += __ldcg(prm.partials + i);
+    tot = block_reduce_to_double(tot, red);
+    if (threadIdx.x == 0) {
+      for (int w = 0; w < W; ++w) {
+        double* slot = reinterpret_cast<double*>(reinterpret_cast<char*>(prm.ctrl[w]) + kCtrlNormByteOffset) + R;
+        asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(slot), "d"(tot) : "memory");
+      }
     }
   });
   dp_wait(prm, 1);
+  stamp(5);
   if (threadIdx.x == 0) {
     const double* slots = reinterpret_cast<const double*>(reinterpret_cast<const char*>(prm.ctrl[R]) + kCtrlNormByteOffset);
     double tot = 0.0;
@@ -337,11 +441,25 @@ dp_apply_kernel(const __grid_constant__ DpParams<CAP> prm) {
   __syncthreads();
   const float s = s_bcast[0];
 
-  // ---- phase C: sharded update + all-gather by pushes (same tile -> block mapping as phase B) -------
-  for (int t = lo + (int)blockIdx.x; t < hi; t += G) dp_update_tile<VARIANT>(prm.tiles[t], prm, s);
+  // ---- phase C: sharded update + all-gather by pushes ----------------------------------------------------
+  {
+    tl.begin(prm.sync + 5, s_ticket);
+    TileDesc d{};
+    if (lo + tl.cur < hi) d = prm.tiles[lo + tl.cur];
+    while (lo + tl.cur < hi) {
+      tl.prefetch();
+      TileDesc dn{};
+      if (lo + tl.nxt < hi) dn = prm.tiles[lo + tl.nxt];
+      dp_update_tile<VARIANT>(d, prm, s);
+      tl.advance();
+      d = dn;
+    }
+  }
+  stamp(6);
   dp_phase_done(prm, 2, [] {});
   // every peer's parameter stores into my slab are complete before the kernel ends
   if (blockIdx.x == 0) dp_wait(prm, 2);
+  stamp(7);
 }
 
 }  // namespace gaccum
