@@ -771,7 +771,7 @@ apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
 #ifdef GACCUM_EXPERIMENTS
         const long long t_e0 = clock64();
 #endif
-        mbar_wait(&s_empty1[grp][rp.slot], (rp.use & 1u) ^ 1u);             // the consumers have released the slot
+        mbar_wait(&s_empty1[grp][rp.slot], rp.use & 1u);             // the consumers have released the slot
 #ifdef GACCUM_EXPERIMENTS
         dbg_empty += clock64() - t_e0;
 #endif
@@ -829,13 +829,13 @@ apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
       }
       if (lane == 0) {
         // end marker, then drain: pass 2's slots overlay pass 1's, so every slot must have been released for the last time
-        mbar_wait(&s_empty1[grp][rp.slot], (rp.use & 1u) ^ 1u);
+        mbar_wait(&s_empty1[grp][rp.slot], rp.use & 1u);
         s_meta1[grp][rp.slot].d.len = 0;
         mbar_arrive(&s_full1[grp][rp.slot]);
         for (int sl = 0; sl < kP1Slots; ++sl) {
           if (sl == rp.slot) continue;
           const uint32_t n = rp.use + (sl < rp.slot ? 1u : 0u);              // times slot sl was armed
-          if (n > 0) mbar_wait(&s_empty1[grp][sl], (n - 1u) & 1u);
+          if (n > 0) mbar_wait(&s_empty1[grp][sl], n & 1u);
         }
       }
       __syncwarp();
@@ -882,7 +882,7 @@ apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
           past_barrier = true;
         }
         uint64_t* full = &s_full2[grp][rp.slot];
-        mbar_wait(&s_empty2[grp][rp.slot], (rp.use & 1u) ^ 1u);
+        mbar_wait(&s_empty2[grp][rp.slot], rp.use & 1u);
         SlotMeta* meta = &s_meta2[grp][rp.slot];
         meta->d = d;
         meta->tmem_slot = in_tmem ? tmem_slot : kNoTmem;
@@ -899,7 +899,7 @@ apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
         }
         rp.advance(kP2Slots);
       }
-      mbar_wait(&s_empty2[grp][rp.slot], (rp.use & 1u) ^ 1u);                   // end marker
+      mbar_wait(&s_empty2[grp][rp.slot], rp.use & 1u);                   // end marker
       s_meta2[grp][rp.slot].d.len = 0;
       mbar_arrive(&s_full2[grp][rp.slot]);
     }
@@ -911,6 +911,12 @@ apply_clip_kernel(const __grid_constant__ KernelParams<CAP> prm) {
     const long long dbg_t0 = clock64();
 #endif
     const bool leader = (threadIdx.x & (kThreads - 1)) == 0;
+    // every slot starts out empty: the consumers say so (phase 0 of each `empty` barrier), so that the producer's very
+    // first wait is an ordinary wait on a phase that completes -- use u of a slot waits for phase u
+    if ((threadIdx.x & 31) == 0) {
+      for (int sl = 0; sl < kP1Slots; ++sl) mbar_arrive(&s_empty1[grp][sl]);
+      for (int sl = 0; sl < kP2Slots; ++sl) mbar_arrive(&s_empty2[grp][sl]);
+    }
     // ---- pass 1: whatever tiles the producer hands over, until its end marker ----
     unsigned int my_nonfinite = 0;
     {
