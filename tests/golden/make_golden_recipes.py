@@ -200,6 +200,68 @@ def run_optimization_case(case, N, init_lr, num_train_steps, num_warmup_steps, s
     return path, edits
 
 
+def bert_small_manifest():
+    """BASELINE config 2 shapes (upstream BERT L4_H512_A8 variable names in creation order; SURVEY.md 8 size table: T=73, P=28 764 674)."""
+    H, L, inter = 512, 4, 2048
+    out = [("bert/embeddings/word_embeddings", (30522, H)), ("bert/embeddings/token_type_embeddings", (2, H)),
+           ("bert/embeddings/position_embeddings", (512, H)), ("bert/embeddings/LayerNorm/beta", (H,)), ("bert/embeddings/LayerNorm/gamma", (H,))]
+    for l in range(L):
+        b = f"bert/encoder/layer_{l}/"
+        for nm in ("query", "key", "value"):
+            out += [(b + f"attention/self/{nm}/kernel", (H, H)), (b + f"attention/self/{nm}/bias", (H,))]
+        out += [(b + "attention/output/dense/kernel", (H, H)), (b + "attention/output/dense/bias", (H,)),
+                (b + "attention/output/LayerNorm/beta", (H,)), (b + "attention/output/LayerNorm/gamma", (H,)),
+                (b + "intermediate/dense/kernel", (H, inter)), (b + "intermediate/dense/bias", (inter,)),
+                (b + "output/dense/kernel", (inter, H)), (b + "output/dense/bias", (H,)),
+                (b + "output/LayerNorm/beta", (H,)), (b + "output/LayerNorm/gamma", (H,))]
+    out += [("bert/pooler/dense/kernel", (H, H)), ("bert/pooler/dense/bias", (H,)), ("output_weights", (2, H)), ("output_bias", (2,))]
+    return out
+
+
+BIG_STRIDE = 4099      # full-size fixture: every 4099th element + fp64 sum of every tensor above SUBSAMPLE_ABOVE
+
+
+def run_optimization_case_full_size(case, N, init_lr, num_train_steps, num_warmup_steps, sigma, seed, steps):
+    """optimization.py (literal at :76 replaced by N) on the BERT-Small shapes of BASELINE config 2.  Gradients and initial
+    values are regenerated from seeds by the consumer; the state after the last two micro-steps is stored subsampled."""
+    tf = _tf()
+    ref, edits = _optimization_module(tf, N_override=N)
+    variables = bert_small_manifest()
+    assert len(variables) == 73 and sum(int(np.prod(s)) for _, s in variables) == 28764674
+    rng = np.random.Generator(np.random.PCG64(SEED0 + 7919 * seed + 100000))
+    _init_vars(tf, variables, rng)
+    train_op = ref.create_optimizer(tf.constant(0.0), init_lr, num_train_steps, num_warmup_steps, False)
+    by_name = {v.name: v for v in tf.global_variables()}
+    grad_ph = {p.name[len("grad/"):]: p for p in tf._g.placeholders}
+    accum_vars = [v for v in tf.global_variables() if v.name.startswith("Variable_")]
+    out = {"names": np.array([n for n, _ in variables]), "shapes": np.array([json.dumps(list(s)) for _, s in variables]),
+           "N": N, "steps": steps, "init_lr": init_lr, "num_train_steps": num_train_steps, "num_warmup_steps": num_warmup_steps,
+           "sigma": sigma, "seed": seed, "stride": BIG_STRIDE}
+
+    def store(key, arr):
+        arr = np.asarray(arr)
+        if arr.size > SUBSAMPLE_ABOVE:
+            out[key + "@sub"] = arr.reshape(-1)[::BIG_STRIDE].copy()
+            out[key + "@sum"] = np.float64(arr.astype(np.float64).sum())
+        else:
+            out[key] = arr.copy()
+    sess = tf.Session()
+    for s in range(steps):
+        gl = grads_for(variables, sigma, seed, s)
+        sess.run(train_op, feed_dict={grad_ph[vname + ":0"]: g for (vname, _), g in zip(variables, gl)})
+        if s >= steps - 2:
+            for i, (vname, _) in enumerate(variables):
+                store(f"param/{s}/{vname}", by_name[vname + ":0"].value)
+                store(f"accum/{s}/{vname}", accum_vars[i].value)
+                store(f"m/{s}/{vname}", by_name[vname + "/adam_m:0"].value)
+                store(f"v/{s}/{vname}", by_name[vname + "/adam_v:0"].value)
+        out[f"global_step/{s}"] = np.int64(by_name["global_step:0"].value)
+    out["recorded_steps"] = np.array([steps - 2, steps - 1])
+    path = os.path.join(HERE, f"ref_fullsize_{case}.npz")
+    np.savez_compressed(path, **out)
+    return path, edits
+
+
 def run_direct_apply_with_none(case, lr, sigma, seed, steps):
     """AdamWeightDecayOptimizer.apply_gradients called directly with a (None, var) pair (optimization.py:132-133)"""
     tf = _tf()
@@ -270,6 +332,13 @@ if __name__ == "__main__":
         meta[case] = {"file": os.path.basename(path), "reference_file": "optimization.py",
                       "edits": [f"line {ln}: literal {old} -> {new} (AST)" for ln, old, new in edits], "config": cfg}
         print("wrote", path, edits)
+    # BASELINE config 2 at full size: accum x4, README schedule shortened so that the run crosses the warm-up end; sigma 1e-3 => clipped
+    path, edits = run_optimization_case_full_size("bert_small_n4", 4, 2e-5, 207900, 6, 1e-3, 41, 10)
+    meta["fullsize_bert_small_n4"] = {"file": os.path.basename(path), "reference_file": "optimization.py",
+                                      "edits": [f"line {ln}: literal {old} -> {new} (AST)" for ln, old, new in edits],
+                                      "shapes": "BERT-Small L4_H512 (T=73, P=28 764 674)", "stored": f"last two micro-steps, every {BIG_STRIDE}th element + fp64 sums",
+                                      "config": [2e-5, 207900, 6, 1e-3, 41, 10]}
+    print("wrote", path)
     path = run_direct_apply_with_none("direct_apply_none_grad", 1e-3, 0.3, 33, 3)
     meta["direct_apply_none_grad"] = {"file": os.path.basename(path), "reference_file": "optimization.py (unmodified)",
                                       "what": "AdamWeightDecayOptimizer.apply_gradients(zip(grads, tvars)) with grads[3] = None (:132-133)"}

@@ -91,7 +91,7 @@ class RecipeGolden:
             assert ok, f"{key} differs from the reference run"
         else:
             sub, tot = self.z[key + "@sub"], float(self.z[key + "@sum"])
-            mine = got.reshape(-1)[::STRIDE]
+            mine = got.reshape(-1)[::getattr(self, "stride", STRIDE)]
             ok = np.array_equal(mine, sub) if exact else np.allclose(mine, sub, rtol=rtol, atol=atol)
             assert ok, f"{key} (subsample) differs from the reference run"
             s = float(got.astype(np.float64).sum())
@@ -103,3 +103,32 @@ class DirectApplyGolden:
         self.z = np.load(os.path.join(GOLDEN_DIR, "ref_direct_apply_none_grad.npz"))
         self.names = [str(n) for n in self.z["names"]]
         self.steps, self.lr, self.none_at = int(self.z["steps"]), float(self.z["lr"]), int(self.z["none_at"])
+
+
+class FullsizeGolden(RecipeGolden):
+    """ref_fullsize_*.npz: the reference's optimization.py (N patched) on BASELINE-sized shapes; gradients and initial
+    values are regenerated from seeds, the last two micro-steps are stored as every `stride`-th element + fp64 sums."""
+
+    def __init__(self, name):
+        import json
+        self.z = np.load(os.path.join(GOLDEN_DIR, f"ref_fullsize_{name}.npz"))
+        self.names = [str(n) for n in self.z["names"]]
+        self.shapes = [tuple(json.loads(str(s))) for s in self.z["shapes"]]
+        self.variables = list(zip(self.names, self.shapes))
+        self.N, self.steps = int(self.z["N"]), int(self.z["steps"])
+        self.init_lr, self.num_train_steps, self.num_warmup_steps = float(self.z["init_lr"]), int(self.z["num_train_steps"]), int(self.z["num_warmup_steps"])
+        self.sigma, self.seed, self.stride = float(self.z["sigma"]), int(self.z["seed"]), int(self.z["stride"])
+        self.recorded = [int(s) for s in self.z["recorded_steps"]]
+
+    def init(self):
+        rng = np.random.Generator(np.random.PCG64(SEED0 + 7919 * self.seed + 100000))
+        out = []
+        for n, shape in self.variables:
+            if n.endswith(("gamma", "scale")):
+                v = np.ones(shape, np.float32)
+            elif n.endswith(("beta", "bias")):
+                v = np.zeros(shape, np.float32)
+            else:
+                v = (rng.standard_normal(shape, dtype=np.float32) * np.float32(0.05)).astype(np.float32)
+            out.append(v)
+        return out

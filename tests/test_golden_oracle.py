@@ -96,3 +96,23 @@ def test_oracle_reproduces_direct_apply_with_none_gradient(impl):
             assert np.array_equal(op.v[k], g.z[f"v/{s}/{n}"])
         skipped = g.names[g.none_at]
         assert np.array_equal(g.z[f"param/{s}/{skipped}"], g.z[f"init/{skipped}"])
+
+
+def test_c_oracle_reproduces_the_reference_at_bert_small_size():
+    """BASELINE config 2 shapes (T=73, P=28.8 M), accum x4, clipped: the reference's optimization.py over the stub vs the
+    C oracle, bit for bit on the stored subsample and fp64 sums (the numpy oracle is bit-identical to the C one)."""
+    from golden_util import FullsizeGolden
+    g = FullsizeGolden("bert_small_n4")
+    assert len(g.names) == 73 and sum(int(np.prod(s)) for s in g.shapes) == 28764674
+    op = oracle_c.COracleTrainOp(g.init(), g.names, onp.HParams.bert(), g.N, init_lr=g.init_lr,
+                                 num_train_steps=g.num_train_steps, num_warmup_steps=g.num_warmup_steps)
+    clipped = 0
+    for s in range(g.steps):
+        info = op.run(g.grads(s))
+        clipped += bool(info.applied and float(info.clip_scale) < 1.0)
+        assert op.global_step == int(g.z[f"global_step/{s}"])
+        if s in g.recorded:
+            for i, n in enumerate(g.names):
+                g.check(f"param/{s}/{n}", op.params[i]); g.check(f"accum/{s}/{n}", op.accum[i])
+                g.check(f"m/{s}/{n}", op.m[i]); g.check(f"v/{s}/{n}", op.v[i])
+    assert clipped >= 2

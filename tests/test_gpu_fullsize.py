@@ -145,3 +145,24 @@ def test_bert_large_properties_pointer_table_1920():
     # every parameter element was updated exactly once: only two distinct values exist overall
     vals = torch.unique(torch.cat([t.flatten()[:: 97] for t in tp]))
     assert vals.numel() == 2
+
+
+def test_bert_small_full_size_against_the_reference_fixture():
+    """The CUDA path on BASELINE config 2 shapes against a fixture produced by the reference's own optimization.py
+    (executed over oracle/tf_stub, N patched to 4): accumulators bit-exact, p / m / v within 1e-5 (every apply clips)."""
+    import gaccum_b200 as g
+    from gaccum_b200.train_op import GaccumTrainOp
+    from golden_util import FullsizeGolden
+    gd = FullsizeGolden("bert_small_n4")
+    tp = [torch.from_numpy(p).cuda() for p in gd.init()]
+    op = GaccumTrainOp(tp, gd.names, g.HParams.bert(), gd.N,
+                       lambda s: g.learning_rate(gd.init_lr, gd.num_train_steps, gd.num_warmup_steps, s))
+    for s in range(gd.steps):
+        op.run([torch.from_numpy(x).cuda() for x in gd.grads(s)])
+        assert op.global_step == int(gd.z[f"global_step/{s}"])
+        if s in gd.recorded:
+            for i, n in enumerate(gd.names):
+                gd.check(f"accum/{s}/{n}", op.accum_view(i).cpu().numpy(), exact=True)
+                gd.check(f"param/{s}/{n}", tp[i].cpu().numpy(), exact=False)
+                gd.check(f"m/{s}/{n}", op.m_view(i).cpu().numpy(), exact=False)
+                gd.check(f"v/{s}/{n}", op.v_view(i).cpu().numpy(), exact=False, atol=1e-12)

@@ -183,6 +183,21 @@ def test_create_optimizer_drop_in_matches_oracle():
     assert l is not None and torch.isfinite(l) and int(graph.get_global_step()) == 19
 
 
+def test_state_dict_uses_the_reference_slot_names_through_the_public_api():
+    """graph.Variable appends ':0' like TF; the reference names slots after _get_variable_name(param.name)
+    (optimization.py:135-148, 189-194): 'scope/kernel/adam_m', never 'scope/kernel:0/adam_m'."""
+    from gaccum_b200 import graph, optimization as opt
+    graph.reset_default_graph()
+    model, rename = _tiny_model()
+    tvars = graph.register_module(model, rename)
+    assert all(v.name.endswith(":0") for v in tvars)
+    train_op = opt.create_optimizer(lambda: model(torch.randn(4, 16, device="cuda")).sum(), 1e-3, 50, 4, False)
+    train_op.run()
+    keys = set(train_op.state_dict())
+    assert {"dense/kernel", "dense/kernel/adam_m", "dense/kernel/adam_v", "dense/kernel/accum_grad", "global_step"} <= keys
+    assert not any(":0" in k for k in keys)
+
+
 def test_inline_recipe_with_tf_adam_like_example_02():
     """distributedExample/02:47-73 -- AdamOptimizer(1e-4), N from params, no clip."""
     from gaccum_b200 import graph, optimization as opt
