@@ -23,9 +23,11 @@ def capture(workload):
     kern = KERNEL[workload]
     log = os.path.join(ROOT, "gpurun_out", f"traffic_{workload}.csv")
     os.makedirs(os.path.dirname(log), exist_ok=True)
+    n_acc = bench.WORKLOADS[workload][1]
+    steps = max(48, 3 * n_acc)                    # at least 3 applies in the timed region, one is skipped
     cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum", "--clock-control", "none",
-           "-k", f"regex:{kern}", "-s", "3", "-c", "4", "--csv", "--log-file", log,
-           sys.executable, os.path.join(ROOT, "bench.py"), "--workload", workload, "--steps", "48", "--warmup", "3",
+           "--profile-from-start", "off", "-k", f"regex:{kern}", "-s", "1", "-c", "2" if n_acc > 8 else "4", "--csv", "--log-file", log,
+           sys.executable, os.path.join(ROOT, "bench.py"), "--workload", workload, "--steps", str(steps), "--warmup", "3",
            "--e2e-steps", "0", "--model-steps", "0", "--cpu-budget", "0", "--parity-steps", "0"]
     subprocess.run(cmd, check=True, cwd=ROOT, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=1200)
     text = open(log).read()
@@ -57,4 +59,4 @@ if __name__ == "__main__":
     for w in wls:
         doc["captures"][w] = capture(w)
         print(w, doc["captures"][w])
-    json.dump(doc, open(path, "w"), indent=1)
+        json.dump(doc, open(path, "w"), indent=1)
