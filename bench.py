@@ -344,13 +344,16 @@ def run_b200_arm(args):
     WU = -(-(W * R) // N) * N
     for i in range(WU):
         micro_step(i)
-    torch.cuda.synchronize(dev)
-    if dist is not None:
-        dist.barrier()
+    # everything slow and rank-dependent (NVML init of the clock sampler, event creation) happens BEFORE the barrier: ranks
+    # must enter the timed loop together, or the early ones spend their first exchange waiting for the latest and that
+    # wait lands in their timed region (8 GPUs: up to 7 ms of a 32 ms region)
     sampler = ClockSampler(local)
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     kinds = []
     sampler.start()
+    torch.cuda.synchronize(dev)
+    if dist is not None:
+        dist.barrier()
     torch.cuda.synchronize(dev)
     base = WU
     torch.cuda.profiler.start()      # ncu --profile-from-start off captures only the timed region

@@ -221,3 +221,20 @@ def test_fused_dp_checkpoint_resume_mid_window(tmp_path):
     for i in range(T):
         assert np.array_equal(r0[f"arr_{i}"], r1[f"arr_{i}"])
         assert np.allclose(r0[f"arr_{i}"], ref.params[i], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_example_04_recipe_under_torchrun():
+    """distributedExample/04 (MultiWorkerMirroredStrategy recipe: 04:13-15, 46, 55-62, 98-121) as a launch script over
+    the fused data-parallel train_op: `torchrun --nproc-per-node 2 examples/mnist_gaccum.py` runs and its loss falls."""
+    import re
+    import subprocess
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port),
+                          os.path.join(ROOT, "examples", "mnist_gaccum.py"), "--steps", "300", "--lr", "1e-3"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    losses = [float(x) for x in re.findall(r"loss ([0-9.]+)", out.stdout)]
+    assert len(losses) >= 3 and losses[-1] < 0.5 * losses[0], out.stdout
