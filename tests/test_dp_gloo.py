@@ -52,6 +52,26 @@ class OracleEngine:
         assert grads is None and self.ref.global_step % self.N == 0
         self.ref.run([None] * len(self.ref.accum))
 
+    # checkpoint surface of GaccumTrainOp (reference names; accumulators read from whatever `accum` currently is)
+    def state_dict(self):
+        out = {"global_step": torch.tensor(self.ref.global_step)}
+        flat = self.accum.numpy()
+        o = 0
+        for i, n in enumerate(self.ref.names):
+            sz = self.ref.params[i].size
+            out[n] = torch.from_numpy(self.ref.params[i].copy())
+            out[n + "/adam_m"] = torch.from_numpy(self.ref.m[i].copy())
+            out[n + "/adam_v"] = torch.from_numpy(self.ref.v[i].copy())
+            out[n + "/accum_grad"] = torch.from_numpy(flat[o:o + sz].reshape(self.ref.params[i].shape).copy())
+            o += sz
+        return out
+
+    def load_state_dict(self, sd, strict=True):
+        self.ref.global_step = int(sd["global_step"])
+        for i, n in enumerate(self.ref.names):
+            self.ref.params[i][...] = sd[n].numpy(); self.ref.m[i][...] = sd[n + "/adam_m"].numpy()
+            self.ref.v[i][...] = sd[n + "/adam_v"].numpy(); self.ref.accum[i][...] = sd[n + "/accum_grad"].numpy()
+
 
 def _grads(rank, step):
     rng = np.random.Generator(np.random.PCG64(19830610 + 1000 * rank + step))
@@ -100,3 +120,51 @@ def test_dp_world2_matches_single_process_on_summed_grads(tmp_path):
         np.testing.assert_allclose(r0[f"arr_{2 * T + i}"], ref.v[i], rtol=1e-5, atol=1e-9)
     # accumulators are rank-local between applies: after step 7 (two accumulate steps) they differ per rank
     assert not np.array_equal(r0[f"arr_{3 * T}"], r1[f"arr_{3 * T}"])
+
+
+def _worker_resume(rank, port, outdir):
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        sys.path.insert(0, p)
+    import oracle_np as onp
+    from gaccum_b200.distributed import DataParallelTrainOp
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=WORLD)
+    names = [n for n, _ in MAN]
+
+    def fresh(fill=None):
+        rng = np.random.default_rng(5)
+        params = [rng.normal(0, 0.02, s).astype(np.float32) if fill is None else np.full(s, fill, np.float32) for _, s in MAN]
+        return onp.ReferenceTrainOp(params, names, onp.HParams.bert(), N, constant_lr=1e-2)
+    ref = fresh()
+    dp = DataParallelTrainOp(OracleEngine(ref), None)
+    for s in range(5):                                   # N = 3: step 3 applied, step 4 only accumulated -> mid-window
+        dp.run(_grads(rank, s))
+    sd = dp.state_dict()                                 # collective: accumulators summed over ranks (04:55 aggregation=SUM)
+    local = float(sum(np.abs(a).sum() for a in ref.accum))
+    summed = float(sum(float(sd[n + "/accum_grad"].abs().sum()) for n in names))
+    ref2 = fresh(fill=9.0)                               # a restarted worker holds garbage until it restores
+    dp2 = DataParallelTrainOp(OracleEngine(ref2), None)
+    dp2.load_state_dict(sd)
+    for s in range(5, STEPS):
+        dp2.run(_grads(rank, s))
+    np.savez(os.path.join(outdir, f"res{rank}.npz"), *ref2.params, local=local, summed=summed, gs=ref2.global_step)
+    dist.destroy_process_group()
+
+
+def test_dp_checkpoint_mid_window_sums_accumulators_and_resumes(tmp_path):
+    """Checkpoint compatibility under data parallelism: the saved accumulators are the SUM over ranks
+    (what the reference's aggregation=SUM variables hold), restored into rank 0 only, and training continues exactly."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    mp.spawn(_worker_resume, args=(port, str(tmp_path)), nprocs=WORLD, join=True)
+    import oracle_np as onp
+    r0, r1 = np.load(tmp_path / "res0.npz"), np.load(tmp_path / "res1.npz")
+    assert float(r0["summed"]) == float(r1["summed"]) and float(r0["summed"]) > max(float(r0["local"]), float(r1["local"]))
+    rng = np.random.default_rng(5)
+    params = [rng.normal(0, 0.02, s).astype(np.float32) for _, s in MAN]
+    ref = onp.ReferenceTrainOp(params, [n for n, _ in MAN], onp.HParams.bert(), N, constant_lr=1e-2)
+    for s in range(STEPS):
+        ref.run([a + b for a, b in zip(_grads(0, s), _grads(1, s))])
+    assert int(r0["gs"]) == STEPS
+    for i in range(len(MAN)):
+        assert np.array_equal(r0[f"arr_{i}"], r1[f"arr_{i}"])
+        np.testing.assert_allclose(r0[f"arr_{i}"], ref.params[i], rtol=1e-5, atol=1e-7)
