@@ -1,10 +1,13 @@
 // gaccum_tf_op.cc -- the `tf.load_op_library` custom ops that put libgaccum.so behind the
 // reference's unchanged `create_optimizer(...)` (reference optimization.py:25-104).
 //
-// NOT BUILT IN THIS REPOSITORY'S IMAGE: TensorFlow (headers and runtime) is absent here
-// (DESIGN.md "Boundary").  What IS exercised here: the C ABI these kernels call, from a plain C++
-// consumer with the same call sequence (tests/abi_consumer.cc), and the Python half of the shim over an
-// emulated op (tests/test_tf_shim_stub.py).  Build where TensorFlow >= 2.4 with tf.compat.v1 exists:
+// NOT BUILT AGAINST TENSORFLOW IN THIS REPOSITORY'S IMAGE: TensorFlow (headers and runtime) is absent here
+// (DESIGN.md "Boundary").  What IS exercised here: this file, unmodified, compiled against a mock of the op-kernel
+// API it uses (tests/tf_mock) and driven by tests/tf_mock/tf_op_driver.cc -- registration, attribute parsing, input
+// indexing, ref / resource variables, HostMemory scalars, error paths on CPU; Compute() -> gaccum_step -> the CUDA
+// kernels against the reference's fixtures on the GPU (tests/test_tf_op_adapter.py); and the Python half of the
+// shim over an emulated op (tests/test_tf_shim_stub.py).  Build where TensorFlow >= 2.11 with tf.compat.v1 exists
+// (se::Stream::platform_specific_handle(); older releases spell it stream->implementation()->GpuStreamHack()):
 //
 //   TF_CFLAGS=$(python -c 'import tensorflow as tf; print(" ".join(tf.sysconfig.get_compile_flags()))')
 //   TF_LFLAGS=$(python -c 'import tensorflow as tf; print(" ".join(tf.sysconfig.get_link_flags()))')
@@ -35,6 +38,7 @@
 #include "tensorflow/core/framework/resource_mgr.h"
 #include "tensorflow/core/framework/resource_var.h"
 #include "tensorflow/core/framework/shape_inference.h"
+#include "tensorflow/core/kernels/training_op_helpers.h"   // PrepareToUpdateVariable
 #include "tensorflow/core/platform/stream_executor.h"
 
 namespace tf = tensorflow;

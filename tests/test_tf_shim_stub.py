@@ -7,7 +7,7 @@ packed state variables, the in-graph learning-rate schedule, which value of ``gl
 update / the increment see, skipping of (None, var) pairs, the 5-argument signature -- reproduces the reference's own
 runs (tests/golden/, produced by the reference's code) bit for bit, in BOTH evaluation orders of unordered op sets
 (``tf.group`` inputs forwards and backwards: a missing control dependency shows up as a difference).
-What it cannot pin: the C++ adapter gaccum_tf_op.cc, which needs TensorFlow's headers (absent from this image)."""
+The C++ adapter gaccum_tf_op.cc is covered separately: tests/test_tf_op_adapter.py (compiled against tests/tf_mock)."""
 import importlib.util
 import inspect
 import os
