@@ -189,10 +189,17 @@ def _worker_fused_resume(rank, world, port, outdir):
         dp.run([torch.from_numpy(x).cuda() for x in _grads(rank, s, world)])
     sd = dp.state_dict()
     assert any(k.endswith("/adam_m") for k in sd) and float(sd["emb/accum_grad"].abs().sum()) > 0
+    # ... and through a TensorFlow-format checkpoint on disk under the reference's Saver names: rank 0 writes, all restore
+    from gaccum_b200 import tf_checkpoint as ck
+    prefix = ck.save(os.path.join(outdir, "model_dir"), dp)
+    assert os.path.exists(prefix + ".index") and os.path.basename(prefix) == "model.ckpt-4"
     del dp
     fresh = [torch.full(s, 7.0, device="cuda") for _, s in MAN]   # a new process would start from garbage
     dp2 = FusedDataParallelTrainOp(fresh, names, g.HParams.bert(), N, lambda s: 1e-2)
-    dp2.load_state_dict(sd)
+    if rank == 0:
+        dp2.load_state_dict(sd)                                   # rank 0 from the in-memory dictionary,
+    else:
+        assert ck.restore(os.path.join(outdir, "model_dir"), dp2) == prefix   # rank 1 from the file: they must agree
     assert dp2.global_step == 4
     for s in range(4, STEPS):
         dp2.run([torch.from_numpy(x).cuda() for x in _grads(rank, s, world)])
