@@ -426,6 +426,58 @@ def from_reference_names(tensors: Dict[str, np.ndarray], names: Sequence[str], v
     return out
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference's per-variable state  <->  the TensorFlow shim's three packed variables (tf_shim/optimization.py)
+# ---------------------------------------------------------------------------------------------------------------------
+def _slab_offsets(sizes: Sequence[int]) -> Tuple[List[int], int]:
+    """Slab layout of include/gaccum.h (gaccum_offsets): every tensor starts at a multiple of 32 elements."""
+    offs, o = [], 0
+    for n in sizes:
+        offs.append(o)
+        o += (int(n) + 31) // 32 * 32
+    return offs, o
+
+
+def to_shim_names(ref: Dict[str, np.ndarray], names: Sequence[str], variant: int, betas=(0.9, 0.999)) -> Dict[str, np.ndarray]:
+    """{reference Saver key: array} -> what a Saver over the shim's graph holds: the parameters and ``global_step``
+    unchanged, ``gaccum/accum_grads`` / ``gaccum/adam_m`` / ``gaccum/adam_v`` packed, ``gaccum/beta_powers``.
+    Lets a checkpoint written by a reference run (mid-window included) be restored into the shim's graph."""
+    m_s, v_s = _SLOTS[variant]
+    sizes = [int(np.asarray(ref[n]).size) for n in names]
+    offs, total = _slab_offsets(sizes)
+    out = {n: np.asarray(ref[n]) for n in names}
+    out["global_step"] = np.asarray(ref.get("global_step", 0), dtype=np.int64)
+    for slab, key in (("gaccum/accum_grads", None), ("gaccum/adam_m", m_s), ("gaccum/adam_v", v_s)):
+        buf = np.zeros(total, np.float32)
+        for i, n in enumerate(names):
+            src = _accum_name(i) if key is None else n + key
+            if src in ref:                                         # a slot the optimizer has not created yet stays zero
+                buf[offs[i]:offs[i] + sizes[i]] = np.asarray(ref[src], np.float32).reshape(-1)
+        out[slab] = buf
+    out["gaccum/beta_powers"] = np.asarray([ref.get("beta1_power", betas[0]), ref.get("beta2_power", betas[1])], np.float32) \
+        if variant == ADAM else np.asarray(betas, np.float32)
+    return out
+
+
+def from_shim_names(shim: Dict[str, np.ndarray], names: Sequence[str], variant: int) -> Dict[str, np.ndarray]:
+    """Inverse of to_shim_names(): a checkpoint of the shim's graph -> the reference's Saver keys."""
+    m_s, v_s = _SLOTS[variant]
+    sizes = [int(np.asarray(shim[n]).size) for n in names]
+    offs, total = _slab_offsets(sizes)
+    out = {n: np.asarray(shim[n]) for n in names}
+    out["global_step"] = np.asarray(shim["global_step"], dtype=np.int64)
+    for slab, key in (("gaccum/accum_grads", None), ("gaccum/adam_m", m_s), ("gaccum/adam_v", v_s)):
+        buf = np.asarray(shim[slab], np.float32).reshape(-1)
+        if buf.size != total:
+            raise ValueError(f"{slab} holds {buf.size} elements, the variables need {total}")
+        for i, n in enumerate(names):
+            out[_accum_name(i) if key is None else n + key] = buf[offs[i]:offs[i] + sizes[i]].reshape(np.asarray(shim[n]).shape).copy()
+    if variant == ADAM:
+        bp = np.asarray(shim["gaccum/beta_powers"], np.float32).reshape(-1)
+        out["beta1_power"], out["beta2_power"] = np.float32(bp[0]), np.float32(bp[1])
+    return out
+
+
 def _engine_of(train_op):
     """The object that knows the variable names and the optimizer variant (wrappers keep it in .engine)."""
     eng = train_op

@@ -120,3 +120,58 @@ def test_shim_direct_apply_gradients_skips_none_pairs(shim):
         for i, n in enumerate(gd.names):
             assert np.array_equal(tvars[i].value, gd.z[f"param/{s}/{n}"]), f"step {s} {n}"
     assert tf.train.get_global_step() is None or int(tf.train.get_global_step().value) == 0     # :99-101: not incremented here
+
+
+# ---- checkpoint interchange between a reference run and the shim's graph ---------------------------------
+def _pick_mid_window(g):
+    """a micro-step after which the reference's accumulators are non-zero (the checkpoint is taken mid-window)"""
+    for s in range(g.N + 1, g.steps - 2):
+        if any(np.any(a != 0) for a in g.state(s, "accum")):
+            return s
+    raise AssertionError("fixture has no mid-window step")
+
+
+def _reference_checkpoint(g, s):
+    """what the reference's Saver holds after micro-step s of the fixture's run (keys: optimization.py:78, 137-148)"""
+    ref = {"global_step": np.asarray(g.global_step(s), np.int64)}
+    for i, n in enumerate(g.names):
+        ref[n] = g.z[f"param/{s}/{n}"]
+        ref[n + "/adam_m"], ref[n + "/adam_v"] = g.z[f"m/{s}/{n}"], g.z[f"v/{s}/{n}"]
+        ref["Variable" if i == 0 else f"Variable_{i}"] = g.z[f"accum/{s}/{n}"]
+    return ref
+
+
+@pytest.mark.parametrize("case", cases())
+def test_reference_checkpoint_restores_into_the_shim_graph_mid_window_and_back(shim, case, tmp_path):
+    """A TF-format checkpoint holding the REFERENCE's state mid-window (taken from the fixture the reference's own code
+    produced) is read back, repacked into the shim's three slab variables and restored into the shim's graph: the rest of
+    the run reproduces the reference's run bit for bit.  And the other way: the shim's variables after the run, mapped
+    to the reference's Saver keys, equal the reference's final state."""
+    from gaccum_b200 import tf_checkpoint as ck
+    tf, mod = shim
+    g = Golden(case)
+    cut = _pick_mid_window(g)
+    prefix = str(tmp_path / f"model.ckpt-{g.global_step(cut)}")
+    ck.write_bundle(prefix, _reference_checkpoint(g, cut))                  # the file a reference run would have left behind
+    restored = ck.to_shim_names(ck.read_bundle(prefix), g.names, ck.ADAM_WEIGHT_DECAY)
+    tf.reset_default_graph()
+    for n, v in zip(g.names, g.init()):
+        tf.get_variable(n, shape=list(v.shape), dtype=tf.float32, initializer=np.full_like(v, 7.0))     # garbage: everything must come from the file
+    mod.gradient_accumulation_multiplier = g.N
+    train_op = mod.create_optimizer(tf.constant(0.0), g.init_lr, g.num_train_steps, g.num_warmup_steps, False)
+    ph = {p.name[len("grad/"):]: p for p in tf._g.placeholders}
+    by = {v.name: v for v in tf.global_variables()}
+    assert set(restored) == {k[:-2] for k in by}                             # exactly the variables a Saver over this graph has
+    for k, arr in restored.items():                                          # == saver.restore(sess, prefix)
+        assert by[k + ":0"].value.shape == arr.shape, k
+        by[k + ":0"].value = arr.astype(by[k + ":0"].value.dtype)
+    sess = tf.Session()
+    for s in range(cut + 1, g.steps):
+        sess.run(train_op, feed_dict={ph[n + ":0"]: x for n, x in zip(g.names, g.grads(s))})
+        for n, exp in zip(g.names, g.state(s, "param")):
+            assert np.array_equal(by[n + ":0"].value, exp), f"{case} resumed at {cut}, step {s} {n}"
+    back = ck.from_shim_names({k[:-2]: v.value for k, v in by.items()}, g.names, ck.ADAM_WEIGHT_DECAY)
+    want = _reference_checkpoint(g, g.steps - 1)
+    assert set(back) == set(want)
+    for k in want:
+        assert np.array_equal(back[k], want[k]), k
