@@ -521,3 +521,38 @@ def restore(prefix_or_dir: str, train_op, names: Optional[Sequence[str]] = None,
     sd = from_reference_names(read_bundle(prefix), names, int(eng.hp.variant), strict)
     train_op.load_state_dict({k: torch.from_numpy(np.array(v, order="C")) for k, v in sd.items()}, strict)
     return prefix
+
+
+def _main(argv: Optional[Sequence[str]] = None) -> int:
+    """python -m gaccum_b200.tf_checkpoint list <prefix|model_dir>
+       python -m gaccum_b200.tf_checkpoint convert {to-shim|to-reference} <in prefix> <out prefix> --names FILE [--variant 0|1]
+    (FILE: one trainable-variable name per line, in tf.trainable_variables() order -- the order is not in a checkpoint)"""
+    import argparse
+    ap = argparse.ArgumentParser(prog="gaccum_b200.tf_checkpoint", description=_main.__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    sub = ap.add_subparsers(dest="cmd", required=True)
+    ls = sub.add_parser("list")
+    ls.add_argument("prefix")
+    cv = sub.add_parser("convert")
+    cv.add_argument("direction", choices=["to-shim", "to-reference"])
+    cv.add_argument("src")
+    cv.add_argument("dst")
+    cv.add_argument("--names", required=True)
+    cv.add_argument("--variant", type=int, default=0, choices=[0, 1])
+    a = ap.parse_args(argv)
+    if a.cmd == "list":
+        prefix = latest_checkpoint(a.prefix) if os.path.isdir(a.prefix) else a.prefix
+        if prefix is None:
+            print(f"no checkpoint state in {a.prefix}")
+            return 1
+        for k, v in sorted(read_bundle(prefix).items(), key=lambda kv: kv[0].encode()):
+            print(f"{k} ({v.dtype.name}) {list(v.shape)}")
+        return 0
+    with open(a.names) as f:
+        names = [ln.strip() for ln in f if ln.strip()]
+    src = read_bundle(a.src)
+    write_bundle(a.dst, to_shim_names(src, names, a.variant) if a.direction == "to-shim" else from_shim_names(src, names, a.variant))
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(_main())

@@ -147,7 +147,7 @@ def test_checkpoint_state_file(tmp_path):
 @pytest.mark.gpu
 @pytest.mark.parametrize("variant", ["adam_weight_decay", "adam"])
 def test_interrupted_run_resumes_from_tf_checkpoint_bit_identically(tmp_path, variant):
-    """Train 2 windows + 1 micro-step, save in the TF format mid-window, restore into a FRESH train_op (fresh tensors),
+    """Train into the 4th window, save in the TF format mid-window, restore into a FRESH train_op (fresh tensors),
     continue: parameters, moments and accumulators equal the uninterrupted run's bit for bit."""
     import torch
     import gaccum_b200 as g
@@ -157,7 +157,7 @@ def test_interrupted_run_resumes_from_tf_checkpoint_bit_identically(tmp_path, va
              "bert/encoder/layer_0/output/LayerNorm/gamma"]
     shapes = [(1000, 64), (64, 300), (300,), (64,)]
     hp = g.HParams.bert() if variant == "adam_weight_decay" else g.HParams.tf_adam()
-    N, total, cut = 3, 11, 7
+    N, total, cut = 3, 12, 8            # windows {0},{1..3},{4..6},{7..9}: after 8 micro-steps g=7 has only accumulated
     rng = np.random.default_rng(3)
     init = [rng.standard_normal(s).astype(np.float32) * 0.02 for s in shapes]
     grads = [[torch.from_numpy(rng.standard_normal(s).astype(np.float32) * 1e-2).to(dev) for s in shapes] for _ in range(total)]
@@ -189,3 +189,42 @@ def test_interrupted_run_resumes_from_tf_checkpoint_bit_identically(tmp_path, va
     assert set(sa) == set(sc)
     for k in sa:
         assert torch.equal(sa[k].cpu(), sc[k].cpu()), k
+
+
+def test_cli_lists_and_converts_between_reference_and_shim_layouts(tmp_path):
+    """python -m gaccum_b200.tf_checkpoint: reference-keyed file -> the shim's packed variables -> back, bit-identical."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = ["a/kernel", "a/LayerNorm/gamma", "a/bias"]
+    rng = np.random.default_rng(2)
+    ref = {"global_step": np.asarray(5, np.int64), "beta1_power": np.float32(0.729), "beta2_power": np.float32(0.997)}
+    for i, (n, shp) in enumerate(zip(names, [(3, 5), (33,), (5,)])):
+        for k in ("", "/Adam", "/Adam_1"):
+            ref[n + k] = rng.standard_normal(shp).astype(np.float32)
+        ref["Variable" if i == 0 else f"Variable_{i}"] = rng.standard_normal(shp).astype(np.float32)
+    ck.write_bundle(str(tmp_path / "ref"), ref)
+    (tmp_path / "names").write_text("\n".join(names) + "\n")
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    run = lambda *a: subprocess.run([sys.executable, "-m", "gaccum_b200.tf_checkpoint", *a], env=env, capture_output=True, text=True, timeout=120)
+    r = run("convert", "to-shim", str(tmp_path / "ref"), str(tmp_path / "shim"), "--names", str(tmp_path / "names"), "--variant", "1")
+    assert r.returncode == 0, r.stderr
+    shim = ck.read_bundle(str(tmp_path / "shim"))
+    assert shim["gaccum/adam_m"].shape == (32 + 64 + 32,)                    # 15 -> 32, 33 -> 64, 5 -> 32: gaccum_offsets' layout
+    assert np.array_equal(shim["gaccum/adam_m"][32:65], ref["a/LayerNorm/gamma/Adam"]) and not shim["gaccum/adam_m"][65:96].any()
+    assert np.array_equal(shim["gaccum/beta_powers"], np.float32([0.729, 0.997]))
+    r = run("list", str(tmp_path / "shim"))
+    assert r.returncode == 0 and "gaccum/accum_grads (float32) [128]" in r.stdout and "global_step (int64) []" in r.stdout
+    r = run("convert", "to-reference", str(tmp_path / "shim"), str(tmp_path / "ref2"), "--names", str(tmp_path / "names"), "--variant", "1")
+    assert r.returncode == 0, r.stderr
+    back = ck.read_bundle(str(tmp_path / "ref2"))
+    assert set(back) == set(ref) and all(np.array_equal(back[k], ref[k]) for k in ref)
+
+
+def test_slab_offsets_agree_with_the_c_abi_layout():
+    import gaccum_b200 as g
+    from gaccum_b200 import _lib
+    sizes = [100, 7, 2048, 1, 33, 0, 4097]
+    plan = _lib.Plan(sizes, None, g.HParams.bert(), device=-1)
+    offs, total = ck._slab_offsets(sizes)
+    assert offs == list(plan.offsets) and total == plan.padded_size
