@@ -496,8 +496,9 @@ def save(model_dir: str, train_op, names: Optional[Sequence[str]] = None, basena
     state = train_op.state_dict()
     step = int(state["global_step"])
     prefix = os.path.join(model_dir, f"{basename}-{step}")
-    group = getattr(train_op, "group", None)
-    world = getattr(train_op, "world", 1)
+    comm = train_op if hasattr(train_op, "world") else getattr(train_op, "dp", None)     # optimization.TrainOp keeps its DP wrapper in .dp
+    group = getattr(comm, "group", None)
+    world = getattr(comm, "world", 1) if comm is not None else 1
     rank = 0
     if world > 1:
         import torch.distributed as dist
