@@ -31,6 +31,8 @@ class OracleEngine:
             ref.accum[i] = flat[o:o + a.size].reshape(a.shape); o += a.size
         self.accum = torch.from_numpy(flat)
         self.N = ref.N
+        self.names = list(ref.names)                      # what tf_checkpoint.save / restore ask the engine for
+        self.hp = type("HP", (), {"variant": 0})()
 
     @property
     def global_step(self):
@@ -141,9 +143,17 @@ def _worker_resume(rank, port, outdir):
     sd = dp.state_dict()                                 # collective: accumulators summed over ranks (04:55 aggregation=SUM)
     local = float(sum(np.abs(a).sum() for a in ref.accum))
     summed = float(sum(float(sd[n + "/accum_grad"].abs().sum()) for n in names))
+    # the same state as a TensorFlow-format checkpoint on disk: every rank calls save(), rank 0 alone writes
+    from gaccum_b200 import tf_checkpoint as ck
+    model_dir = os.path.join(outdir, "model_dir")
+    prefix = ck.save(model_dir, dp)
+    assert os.path.exists(prefix + ".index") and sorted(os.listdir(model_dir)) == ["checkpoint", "model.ckpt-5.data-00000-of-00001", "model.ckpt-5.index"]
     ref2 = fresh(fill=9.0)                               # a restarted worker holds garbage until it restores
     dp2 = DataParallelTrainOp(OracleEngine(ref2), None)
-    dp2.load_state_dict(sd)
+    if rank == 0:
+        dp2.load_state_dict(sd)                          # rank 0 from the in-memory dictionary, rank 1 from the file
+    else:
+        assert ck.restore(model_dir, dp2) == prefix
     for s in range(5, STEPS):
         dp2.run(_grads(rank, s))
     np.savez(os.path.join(outdir, f"res{rank}.npz"), *ref2.params, local=local, summed=summed, gs=ref2.global_step)
